@@ -1,0 +1,214 @@
+/*
+ * agentgo_b200.h — C ABI of the B200-native flat Monte-Carlo playout engine.
+ *
+ * This library is a drop-in for ONE path of Menooker/AgentGo: the random-playout
+ * evaluation behind GTP `genmove`.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference checkout).
+ *
+ *   reference                                           replaced by
+ *   --------------------------------------------------  ---------------------------
+ *   Scheduler<MyWorker>(true)      TinyMT.h:733         agb_create
+ *   ~Scheduler                     TinyMT.h:739         agb_destroy
+ *   GTPAdapter::bd.clear()         GTPAdapter.cpp:151   agb_clear_board
+ *   onBoardSize(int)               GTPAdapter.h:16      agb_boardsize
+ *   bd.put(colour,a,b)             GTPAdapter.cpp:78,92 agb_play
+ *   Board::pass                    Board.cpp:200        agb_pass
+ *   submit(MyJob)+go()+wait()      AgentGo.cpp:595-605  agb_playouts   (C >= 1)
+ *   MyWorker::work playout loop    AgentGo.cpp:285-327  agb_playouts   (C >= 1)
+ *   MyGame::testAvrgWin            AgentGo.cpp:412-448  agb_playouts   (C == 0, "root mode")
+ *   MyGame::onMove (step>4 branch) AgentGo.cpp:573-688  agb_genmove
+ *   Board::check*                  Board.cpp:480-755    agb_check
+ *   Board::countScore              Board.cpp:910        agb_count_score
+ *
+ * Conventions
+ *   - plain C, no C++ types, no exceptions across the boundary;
+ *   - every call returns AGB_OK (0) or a negative agb_status; agb_last_error()
+ *     gives the text of the last failure on that engine;
+ *   - an engine is NOT thread-safe: one caller thread, like the reference's
+ *     single GTP thread;
+ *   - the caller owns every buffer it passes in; results are complete when the
+ *     call returns (the stream is synchronised inside);
+ *   - colours: 0 empty, 1 black, 2 white (GoContest/AgentGo.h:11-13);
+ *     a point is (row, col), idx = row*N + col (Board.cpp:100);
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails
+ *     with AGB_ERR_CUDA.
+ *
+ * Randomness.  The reference draws from libc rand(); this
+ * build injects one TinyMT32 generator (RFC 8682) per playout, in both the
+ * oracle and the kernels:  rand() := tinymt32_uint32() >> 17   (15 bit, the
+ * range of the reference platform's RAND_MAX = 0x7fff).  The per-playout seed
+ * is the pure function agb_playout_seed() below, so the partition of playouts
+ * over threads, blocks or GPUs can never change a result.
+ */
+#ifndef AGENTGO_B200_H_
+#define AGENTGO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGB_VERSION_MAJOR 0
+#define AGB_VERSION_MINOR 1
+
+#define AGB_MAX_BOARD_SIZE 19
+#define AGB_MAX_POINTS (AGB_MAX_BOARD_SIZE * AGB_MAX_BOARD_SIZE)
+
+#define AGB_EMPTY 0
+#define AGB_BLACK 1
+#define AGB_WHITE 2
+
+/* TinyMT32 parameter set of RFC 8682 */
+#define AGB_TINYMT_MAT1 0x8f7011eeu
+#define AGB_TINYMT_MAT2 0xfc78ff1fu
+#define AGB_TINYMT_TMAT 0x3793fdffu
+
+/* candidate index used in the seed tuple by root-mode playouts (C == 0) */
+#define AGB_ROOT_CANDIDATE 0xffffffffu
+
+typedef enum agb_status {
+    AGB_OK = 0,
+    AGB_ERR_INVALID = -1,   /* bad argument (size, colour, coordinates, NULL) */
+    AGB_ERR_OCCUPIED = -2,  /* agb_play on an occupied point (reference: AG_PANIC, Board.cpp:75-78) */
+    AGB_ERR_CUDA = -3,      /* CUDA runtime error or no device */
+    AGB_ERR_NOMEM = -4,
+    AGB_ERR_FAULT = -5,     /* a playout hit the per-playout move cap (fault detector only) */
+    AGB_ERR_STATE = -6      /* call not valid in this state */
+} agb_status;
+
+/* kernel selector: the mapping of playouts onto the machine */
+typedef enum agb_kernel {
+    AGB_KERNEL_AUTO = 0,
+    AGB_KERNEL_THREAD = 1,  /* one thread per playout */
+    AGB_KERNEL_WARP = 2     /* one warp per playout   */
+} agb_kernel;
+
+typedef struct agb_config {
+    int board_size;      /* 9, 13 or 19 */
+    int device;          /* CUDA device ordinal */
+    int kernel;          /* agb_kernel */
+    int shard_rank;      /* this engine evaluates global playout ids g with        */
+    int shard_count;     /*   g % shard_count == shard_rank   (1 => everything)     */
+    uint32_t mat1, mat2, tmat; /* TinyMT32 parameters; 0,0,0 => RFC 8682 set      */
+    int max_moves;       /* per-playout move cap, 0 => default (fault detector)    */
+} agb_config;
+
+typedef struct agb_engine agb_engine;
+
+/* statistics of the last agb_playouts* call */
+typedef struct agb_stats {
+    float device_ms;        /* CUDA-event time of the kernel(s) on the engine's stream */
+    int64_t playouts;       /* playouts this engine ran (its shard)                    */
+    int64_t moves;          /* stones placed in those playouts                         */
+    int64_t rng_draws;      /* rand() calls consumed                                   */
+    int32_t kernel_launches;
+    int32_t faults;         /* playouts stopped by the move cap                        */
+} agb_stats;
+
+/* one position of a batch: a move list replayed from the empty board.
+ * moves[i] = colour<<16 | row<<8 | col ; row = col = 0xff encodes pass. */
+typedef struct agb_position {
+    const uint32_t* moves;
+    int32_t n_moves;
+    int32_t to_move;        /* colour whose root-mode playouts are evaluated */
+} agb_position;
+
+#define AGB_MOVE(colour, row, col) \
+    (((uint32_t)(colour) << 16) | ((uint32_t)((row) & 0xff) << 8) | (uint32_t)((col) & 0xff))
+#define AGB_MOVE_PASS(colour) AGB_MOVE(colour, 0xff, 0xff)
+
+/* ---- life cycle ------------------------------------------------------- */
+void agb_default_config(agb_config* cfg);
+int agb_create(const agb_config* cfg, agb_engine** out);
+void agb_destroy(agb_engine* h);
+const char* agb_last_error(const agb_engine* h);
+const char* agb_version(void);
+int agb_device_count(void);
+
+/* ---- position (host-side replay into the exact reference state) ------- */
+int agb_boardsize(agb_engine* h, int n);             /* also clears the board */
+int agb_clear_board(agb_engine* h);
+int agb_play(agb_engine* h, int colour, int row, int col);
+int agb_pass(agb_engine* h, int colour);
+int agb_get_board(const agb_engine* h, uint8_t* colours /* N*N */, int* n);
+
+/* which: 0 suicide, 1 kill, 2 survive, 3 dying, 4 chase, 5 true eye, 6 compete (ko),
+ *        7 no-sense.   returns 0/1, or <0 on error.                          */
+int agb_check(const agb_engine* h, int which, int colour, int row, int col);
+int agb_count_score(const agb_engine* h, int colour);
+
+/* debugging / parity: dump the full compact state as int32 words;
+ * returns the number of words written, or <0.                               */
+int agb_export_state(const agb_engine* h, int32_t* out, int cap);
+
+/* ---- the hot path ------------------------------------------------------
+ * colour   : the side the evaluation is for ("agent" = isWh+1, AgentGo.cpp:78)
+ * cand_rc  : C pairs (row, col).  C >= 1: for each candidate, play it for `colour`,
+ *            then P playouts with the ENEMY moving first (AgentGo.cpp:300,310).
+ *            C == 0 (cand_rc may be NULL): root mode, P playouts with `colour`
+ *            moving first (AgentGo.cpp:425,434); outputs have one element.
+ * P        : playouts per candidate.  Global playout id g = cand*P + p; this
+ *            engine runs those with g % shard_count == shard_rank.
+ * avrg_win : threshold subtracted from every diff (AgentGo.cpp:327).
+ * seed_base: 64-bit base of the per-playout seed tuple (agb_playout_seed).
+ * position_id : enters the seed tuple (0 for the engine's own board).
+ * wins/sum_pos/sum_neg [max(C,1)] : with w = diff - avrg_win per playout,
+ *            wins = #{w >= 0}, sum_pos = sum max(w,0), sum_neg = sum min(w,0)
+ *            — this engine's SHARD only (sum them over shards; agb_counters_dev
+ *            exposes the same numbers on the device for an NCCL allreduce).
+ * per_playout_diff [max(C,1)*P] or NULL : diff = countScore(colour) -
+ *            countScore(enemy) of every playout of this shard; entries of
+ *            other shards are left untouched.
+ */
+int agb_playouts(agb_engine* h, int colour, const int16_t* cand_rc, int C, int64_t P,
+                 int avrg_win, uint64_t seed_base, uint32_t position_id,
+                 int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
+                 int16_t* per_playout_diff, agb_stats* stats);
+
+/* Asynchronous halves of agb_playouts for callers that own the collective:
+ * launch leaves the 3*max(C,1) int64 counters [wins | sum_pos | sum_neg] in
+ * device memory (agb_counters_dev), finish synchronises and copies out.      */
+int agb_playouts_launch(agb_engine* h, int colour, const int16_t* cand_rc, int C, int64_t P,
+                        int avrg_win, uint64_t seed_base, uint32_t position_id,
+                        int want_diffs);
+int agb_playouts_finish(agb_engine* h, int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
+                        int16_t* per_playout_diff, agb_stats* stats);
+/* device pointer (int64[3*max(C,1)]) and CUDA stream (cudaStream_t as void*) */
+void* agb_counters_dev(agb_engine* h);
+void* agb_stream(agb_engine* h);
+
+/* batch of B independent positions (config 3): root-mode, P playouts each,
+ * position b uses position_id = first_position_id + b and is evaluated by the
+ * shard with (first_position_id + b) % shard_count == shard_rank.
+ * outputs are [B]; per_playout_diff is [B*P] or NULL.                        */
+int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
+                       uint64_t seed_base, uint32_t first_position_id,
+                       int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
+                       int16_t* per_playout_diff, agb_stats* stats);
+
+/* GTP-compat genmove (AgentGo.cpp:573-688 without the static heuristics and
+ * AMAF terms, which are outside the flat-MC path): root playouts -> avrg_win,
+ * candidate filter, P playouts per candidate, argmax of
+ * sum_pos + cnsv*sum_neg.  *is_pass = 1 when no candidate exists.  The move
+ * is NOT played on the engine's board (the caller does, GTPAdapter.cpp:78). */
+int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_root,
+                uint64_t seed_base, int* row, int* col, int* is_pass, agb_stats* stats);
+
+/* ---- the seed contract (shared verbatim by oracle and kernels) --------- */
+static inline uint32_t agb_playout_seed(uint64_t seed_base, uint32_t position_id,
+                                        uint32_t candidate_idx, uint64_t playout_idx) {
+    uint64_t z = seed_base;
+    z += 0x9E3779B97F4A7C15ull * (playout_idx + 1);
+    z ^= 0xBF58476D1CE4E5B9ull * ((uint64_t)candidate_idx + 1);
+    z += 0x94D049BB133111EBull * ((uint64_t)position_id + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z ^ (z >> 32));
+}
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGENTGO_B200_H_ */
