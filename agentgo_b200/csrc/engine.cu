@@ -1,0 +1,333 @@
+// engine.cu — see engine.h
+#include "engine.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+
+namespace agb {
+
+static const size_t kSmallWords = 8;   // [0] work counter, [1..4] stats
+
+int Engine::cuda_fail(cudaError_t e, const char* what) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+    return fail(AGB_ERR_CUDA, buf);
+}
+
+#define AGB_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+int Engine::create(const agb_config& cfg, Engine** out, std::string* err) {
+    *out = nullptr;
+    if (!HostBoard::size_supported(cfg.board_size)) {
+        if (err) *err = "board_size must be 9, 13 or 19";
+        return AGB_ERR_INVALID;
+    }
+    if (cfg.shard_count < 1 || cfg.shard_rank < 0 || cfg.shard_rank >= cfg.shard_count) {
+        if (err) *err = "bad shard_rank/shard_count";
+        return AGB_ERR_INVALID;
+    }
+    if (cfg.device == -1) {
+        // position-only engine: replay / predicates / export work, every compute call fails
+        Engine* h = new Engine();
+        h->cfg = cfg;
+        h->board.reset(cfg.board_size);
+        *out = h;
+        return AGB_OK;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        // no CPU fallback by design: the product path fails loudly without a GPU
+        if (err) *err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return AGB_ERR_CUDA;
+    }
+    if (cfg.device < 0 || cfg.device >= ndev) {
+        if (err) *err = "device ordinal out of range";
+        return AGB_ERR_INVALID;
+    }
+    Engine* h = new Engine();
+    h->cfg = cfg;
+    if (h->cfg.mat1 == 0 && h->cfg.mat2 == 0 && h->cfg.tmat == 0) {
+        h->cfg.mat1 = AGB_TINYMT_MAT1; h->cfg.mat2 = AGB_TINYMT_MAT2; h->cfg.tmat = AGB_TINYMT_TMAT;
+    }
+    if (h->cfg.max_moves <= 0) h->cfg.max_moves = kDefaultMaxMoves;
+    h->board.reset(cfg.board_size);
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(cfg.device)) != cudaSuccess ||
+        (e = cudaGetDeviceProperties(&prop, cfg.device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&h->stream_, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev0_)) != cudaSuccess || (e = cudaEventCreate(&h->ev1_)) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_small_, kSmallWords * sizeof(unsigned long long))) != cudaSuccess) {
+        if (err) *err = std::string("CUDA init: ") + cudaGetErrorString(e);
+        delete h;
+        return AGB_ERR_CUDA;
+    }
+    h->sm_count_ = prop.multiProcessorCount;
+    *out = h;
+    return AGB_OK;
+}
+
+Engine::~Engine() {
+    if (cfg.device < 0) return;
+    cudaSetDevice(cfg.device);
+    if (stream_) cudaStreamSynchronize(stream_);
+    cudaFree(d_starts_); cudaFree(d_descs_); cudaFree(d_counters_); cudaFree(d_diffs_);
+    cudaFree(d_small_);
+    if (h_pinned_) cudaFreeHost(h_pinned_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+int Engine::ensure(void** ptr, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return AGB_OK;
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    cudaError_t e = cudaMalloc(ptr, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(AGB_ERR_NOMEM, "cudaMalloc failed"); }
+    *cap = want;
+    return AGB_OK;
+}
+
+int Engine::launch(const std::vector<Position>& starts, const std::vector<StartDesc>& descs, int64_t P,
+                   uint64_t seed_base, bool want_diffs, bool shard_units) {
+    if (cfg.device < 0) return fail(AGB_ERR_CUDA, "engine was created without a CUDA device (device = -1); no CPU fallback");
+    if (in_flight_) return fail(AGB_ERR_STATE, "a launch is already in flight");
+    if (starts.empty() || starts.size() != descs.size() || P <= 0)
+        return fail(AGB_ERR_INVALID, "nothing to launch");
+    AGB_CUDA(cudaSetDevice(cfg.device));
+    const int S = (int)starts.size();
+    int st;
+    if ((st = ensure(&d_starts_, &cap_starts_, sizeof(Position) * (size_t)S))) return st;
+    if ((st = ensure(&d_descs_, &cap_descs_, sizeof(StartDesc) * (size_t)S))) return st;
+    if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)S))) return st;
+    if (want_diffs && (st = ensure(&d_diffs_, &cap_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P))) return st;
+
+    AGB_CUDA(cudaMemcpyAsync(d_starts_, starts.data(), sizeof(Position) * (size_t)S, cudaMemcpyHostToDevice, stream_));
+    AGB_CUDA(cudaMemcpyAsync(d_descs_, descs.data(), sizeof(StartDesc) * (size_t)S, cudaMemcpyHostToDevice, stream_));
+    AGB_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(long long) * 3 * (size_t)S, stream_));
+    AGB_CUDA(cudaMemsetAsync(d_small_, 0, kSmallWords * sizeof(unsigned long long), stream_));
+
+    KernelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.starts = (const Position*)d_starts_;
+    a.descs = (const StartDesc*)d_descs_;
+    a.n_starts = S;
+    a.P = P;
+    a.seed_base = seed_base;
+    a.shard_rank = shard_units ? cfg.shard_rank : 0;
+    a.shard_count = shard_units ? cfg.shard_count : 1;
+    const int64_t total = (int64_t)S * P;
+    a.local_units = total > a.shard_rank ? (total - a.shard_rank + a.shard_count - 1) / a.shard_count : 0;
+    a.work_counter = (unsigned long long*)d_small_;
+    a.stats = (unsigned long long*)d_small_ + 1;
+    a.counters = (long long*)d_counters_;
+    a.diffs = want_diffs ? (int16_t*)d_diffs_ : nullptr;
+    a.rng.mat1 = cfg.mat1; a.rng.mat2 = cfg.mat2; a.rng.tmat = cfg.tmat;
+    a.max_moves = cfg.max_moves;
+
+    AGB_CUDA(cudaEventRecord(ev0_, stream_));
+    if (a.local_units > 0) {
+        cudaError_t e;
+        const int n = board.n();
+        if (cfg.kernel == AGB_KERNEL_THREAD) e = launch_playout_thread(n, a, sm_count_, stream_, &info_);
+        else e = launch_playout_warp(n, a, sm_count_, stream_, &info_);
+        if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    }
+    AGB_CUDA(cudaEventRecord(ev1_, stream_));
+    in_flight_ = true;
+    n_starts_ = S; P_ = P; want_diffs_ = want_diffs; shard_units_ = shard_units;
+    return AGB_OK;
+}
+
+int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats) {
+    if (!in_flight_) return fail(AGB_ERR_STATE, "no launch in flight");
+    in_flight_ = false;
+    AGB_CUDA(cudaSetDevice(cfg.device));
+    const int S = n_starts_;
+    // snapshot the shard-local stats before any collective touches the counters
+    const size_t need = sizeof(long long) * 3 * (size_t)S + kSmallWords * sizeof(unsigned long long);
+    if (cap_pinned_ < need) {
+        if (h_pinned_) cudaFreeHost(h_pinned_);
+        h_pinned_ = nullptr; cap_pinned_ = 0;
+        AGB_CUDA(cudaMallocHost(&h_pinned_, need));
+        cap_pinned_ = need;
+    }
+    if (allreduce_) {
+        int r = allreduce_(allreduce_ctx_, d_counters_, 3 * S, (void*)stream_);
+        if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
+    }
+    long long* hc = (long long*)h_pinned_;
+    unsigned long long* hs = (unsigned long long*)(hc + 3 * (size_t)S);
+    AGB_CUDA(cudaMemcpyAsync(hc, d_counters_, sizeof(long long) * 3 * (size_t)S, cudaMemcpyDeviceToHost, stream_));
+    AGB_CUDA(cudaMemcpyAsync(hs, d_small_, kSmallWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    if (diffs && want_diffs_ && !(shard_units_ && cfg.shard_count > 1))
+        AGB_CUDA(cudaMemcpyAsync(diffs, d_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P_, cudaMemcpyDeviceToHost, stream_));
+    AGB_CUDA(cudaStreamSynchronize(stream_));
+    if (diffs && want_diffs_ && shard_units_ && cfg.shard_count > 1) {
+        // only this shard's entries are defined on the device; leave the others untouched
+        std::vector<int16_t> tmp((size_t)S * (size_t)P_);
+        AGB_CUDA(cudaMemcpy(tmp.data(), d_diffs_, sizeof(int16_t) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int64_t g = cfg.shard_rank; g < (int64_t)tmp.size(); g += cfg.shard_count) diffs[g] = tmp[g];
+    }
+    for (int s = 0; s < S; s++) {
+        if (wins) wins[s] = hc[s];
+        if (sum_pos) sum_pos[s] = hc[S + s];
+        if (sum_neg) sum_neg[s] = hc[2 * S + s];
+    }
+    float ms = 0.f;
+    AGB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    const unsigned long long* stv = hs + 1;
+    if (stats) {
+        stats->device_ms = ms;
+        stats->moves = (int64_t)stv[kStatMoves];
+        stats->rng_draws = (int64_t)stv[kStatDraws];
+        stats->faults = (int32_t)stv[kStatFaults];
+        stats->playouts = (int64_t)stv[kStatPlayouts];
+        stats->kernel_launches = 1;
+    }
+    if (stv[kStatFaults] != 0) return fail(AGB_ERR_FAULT, "a playout exceeded the move cap");
+    return AGB_OK;
+}
+
+int Engine::playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P, int avrg_win,
+                            uint64_t seed_base, uint32_t position_id, bool want_diffs) {
+    if (colour != AGB_BLACK && colour != AGB_WHITE) return fail(AGB_ERR_INVALID, "bad colour");
+    if (C < 0 || (C > 0 && !cand_rc) || P <= 0) return fail(AGB_ERR_INVALID, "bad candidates or P");
+    const int n = board.n();
+    std::vector<Position> starts;
+    std::vector<StartDesc> descs;
+    if (C == 0) {
+        // root mode = MyGame::testAvrgWin (AgentGo.cpp:412-448): the mover plays first
+        starts.push_back(board.position());
+        StartDesc d = {position_id, AGB_ROOT_CANDIDATE, (int16_t)colour, (int16_t)colour, avrg_win};
+        descs.push_back(d);
+    } else {
+        starts.reserve(C);
+        for (int c = 0; c < C; c++) {
+            const int row = cand_rc[2 * c], col = cand_rc[2 * c + 1];
+            if (row < 0 || col < 0 || row >= n || col >= n) return fail(AGB_ERR_INVALID, "candidate off board");
+            if (board.colour_at(row * n + col) != 0) return fail(AGB_ERR_OCCUPIED, "candidate point occupied");
+            // MyWorker::work (AgentGo.cpp:83): candidate played, then the enemy moves first (:300,310)
+            starts.push_back(board.with_move(colour, row * n + col));
+            StartDesc d = {position_id, (uint32_t)c, (int16_t)colour, (int16_t)(3 - colour), avrg_win};
+            descs.push_back(d);
+        }
+    }
+    return launch(starts, descs, P, seed_base, want_diffs, true);
+}
+
+int Engine::playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t seed_base,
+                           uint32_t first_position_id, int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
+                           int16_t* diffs, agb_stats* stats) {
+    if (!pos || B <= 0 || P <= 0) return fail(AGB_ERR_INVALID, "bad batch");
+    std::vector<Position> starts;
+    std::vector<StartDesc> descs;
+    std::vector<int> owner;     // batch index of each local start
+    HostBoard hb(board.n());
+    for (int b = 0; b < B; b++) {
+        const uint32_t pid = first_position_id + (uint32_t)b;
+        if ((int)(pid % (uint32_t)cfg.shard_count) != cfg.shard_rank) continue;
+        hb.clear();
+        int st = hb.replay(pos[b].moves, pos[b].n_moves);
+        if (st) return fail(st == -2 ? AGB_ERR_OCCUPIED : AGB_ERR_INVALID, "bad move list in batch");
+        const int colour = pos[b].to_move;
+        if (colour != AGB_BLACK && colour != AGB_WHITE) return fail(AGB_ERR_INVALID, "bad to_move");
+        starts.push_back(hb.position());
+        StartDesc d = {pid, AGB_ROOT_CANDIDATE, (int16_t)colour, (int16_t)colour, 0};
+        descs.push_back(d);
+        owner.push_back(b);
+    }
+    for (int b = 0; b < B; b++) {
+        if (wins) wins[b] = 0;
+        if (sum_pos) sum_pos[b] = 0;
+        if (sum_neg) sum_neg[b] = 0;
+    }
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (starts.empty()) return AGB_OK;
+    const int S = (int)starts.size();
+    int st = launch(starts, descs, P, seed_base, diffs != nullptr, false);
+    if (st) return st;
+    std::vector<int64_t> w(S), sp(S), sn(S);
+    std::vector<int16_t> dl;
+    if (diffs) dl.resize((size_t)S * (size_t)P);
+    AllreduceFn saved = allreduce_;
+    allreduce_ = nullptr;       // results of a batch are gathered by the caller, per position
+    st = finish(w.data(), sp.data(), sn.data(), diffs ? dl.data() : nullptr, stats);
+    allreduce_ = saved;
+    if (st) return st;
+    for (int s = 0; s < S; s++) {
+        const int b = owner[s];
+        if (wins) wins[b] = w[s];
+        if (sum_pos) sum_pos[b] = sp[s];
+        if (sum_neg) sum_neg[b] = sn[s];
+        if (diffs) memcpy(diffs + (size_t)b * (size_t)P, dl.data() + (size_t)s * (size_t)P, sizeof(int16_t) * (size_t)P);
+    }
+    return AGB_OK;
+}
+
+// MyGame::onMove, step > 4 branch (AgentGo.cpp:573-688), flat-MC terms only:
+//   avrg_win = testAvrgWin (:579), candidate filter (:586-592), playouts per candidate,
+//   mc[i][j] = 100*index_c * sum(score), score = w >= 0 ? w : w*cnsv, cnsv = 2^(avrg_win*index_cnsv)
+//   (:99,:328,:340), argmax with first-wins ties in row-major order (:647-676).
+// Static heuristics (:104-282) and AMAF (:329-338) are outside the flat-MC path.
+int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_base, int* row, int* col,
+                    int* is_pass, agb_stats* stats) {
+    if (colour != AGB_BLACK && colour != AGB_WHITE) return fail(AGB_ERR_INVALID, "bad colour");
+    if (cfg.shard_count > 1 && !allreduce_)
+        return fail(AGB_ERR_STATE, "genmove on a sharded engine needs an allreduce callback");
+    const int n = board.n();
+    agb_stats acc, st1;
+    memset(&acc, 0, sizeof(acc));
+    int64_t w = 0, sp = 0, sn = 0;
+    int st = playouts_launch(colour, nullptr, 0, P_root, 0, seed_base, 0, false);
+    if (st) return st;
+    if ((st = finish(&w, &sp, &sn, nullptr, &st1))) return st;
+    acc = st1;
+    const int avrg_win = (int)((sp + sn) / P_root);          // C truncation, AgentGo.cpp:447
+    std::vector<int16_t> cand;
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++)
+            if (board.is_candidate(colour, i, j)) { cand.push_back((int16_t)i); cand.push_back((int16_t)j); }
+    const int C = (int)cand.size() / 2;
+    *is_pass = 1; *row = -1; *col = -1;
+    if (C > 0) {
+        std::vector<int64_t> cw(C), csp(C), csn(C);
+        st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false);
+        if (st) return st;
+        if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1))) return st;
+        acc.device_ms += st1.device_ms; acc.playouts += st1.playouts; acc.moves += st1.moves;
+        acc.rng_draws += st1.rng_draws; acc.kernel_launches += st1.kernel_launches;
+        const double cnsv = std::pow(2.0, avrg_win * 0.01);  // index_cnsv = 0.01, AgentGo.cpp:25,99
+        // argmax over every eligible point in row-major order, first maximum wins (:647-676).
+        // Points the candidate filter dropped only for checkNoSense still compete with mark 0.
+        bool init = false;
+        double best = 0;
+        int c = 0;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                const bool is_cand = c < C && cand[2 * c] == i && cand[2 * c + 1] == j;
+                double mark = 0;
+                if (is_cand) {
+                    // total_mark gets every score once (:339) and mc again (:653)
+                    mark = 2.0 * 100.0 * ((double)csp[c] + cnsv * (double)csn[c]);
+                    c++;
+                }
+                if (!board.is_eligible(colour, i, j)) continue;
+                if (!init || mark > best) { best = mark; *row = i; *col = j; init = true; }
+            }
+        *is_pass = 0;
+    }
+    if (stats) *stats = acc;
+    return AGB_OK;
+}
+
+}  // namespace agb

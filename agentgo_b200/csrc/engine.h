@@ -1,0 +1,78 @@
+// engine.h — the object behind the C ABI (include/agentgo_b200.h).
+//
+// Replaces the CpuCount-driven thread pool the reference builds per genmove
+// (Scheduler<MyWorker>, TinyMT.h:460-866; AgentGo.cpp:576-609): instead of 2*cores+2 worker
+// threads pulling MyJobs, one persistent CUDA kernel pulls playout ids.
+#ifndef AGB_ENGINE_H_
+#define AGB_ENGINE_H_
+
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "agentgo_b200.h"
+#include "host_board.h"
+#include "kernel_args.h"
+
+namespace agb {
+
+typedef int (*AllreduceFn)(void* ctx, void* dev_int64, int count, void* cuda_stream);
+
+class Engine {
+public:
+    static int create(const agb_config& cfg, Engine** out, std::string* err);
+    ~Engine();
+
+    HostBoard board;
+    std::string err;
+    agb_config cfg;
+
+    // general launch: starts x P playouts, ids sharded by g % shard_count (by_unit) or all local
+    int launch(const std::vector<Position>& starts, const std::vector<StartDesc>& descs, int64_t P,
+               uint64_t seed_base, bool want_diffs, bool shard_units);
+    // waits, copies counters (and diffs) out.  Buffers are [n_starts] / [n_starts*P].
+    int finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats);
+
+    int playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P, int avrg_win,
+                        uint64_t seed_base, uint32_t position_id, bool want_diffs);
+    int playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t seed_base,
+                       uint32_t first_position_id, int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
+                       int16_t* diffs, agb_stats* stats);
+    int genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_base, int* row, int* col,
+                int* is_pass, agb_stats* stats);
+
+    void* counters_dev() const { return d_counters_; }
+    cudaStream_t stream() const { return stream_; }
+    void set_allreduce(AllreduceFn fn, void* ctx) { allreduce_ = fn; allreduce_ctx_ = ctx; }
+    int fail(int status, const std::string& msg) { err = msg; return status; }
+
+private:
+    Engine() : board(13) {}
+    int ensure(void** ptr, size_t* cap, size_t bytes);
+    int cuda_fail(cudaError_t e, const char* what);
+
+    int sm_count_ = 0;
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    void* d_starts_ = nullptr; size_t cap_starts_ = 0;
+    void* d_descs_ = nullptr; size_t cap_descs_ = 0;
+    void* d_counters_ = nullptr; size_t cap_counters_ = 0;
+    void* d_diffs_ = nullptr; size_t cap_diffs_ = 0;
+    void* d_small_ = nullptr;            // work counter + stats
+    void* h_pinned_ = nullptr; size_t cap_pinned_ = 0;
+
+    // state of the launch in flight
+    bool in_flight_ = false;
+    int n_starts_ = 0;
+    int64_t P_ = 0;
+    bool want_diffs_ = false;
+    bool shard_units_ = false;
+    LaunchInfo info_ = {0, 0, 0, ""};
+    AllreduceFn allreduce_ = nullptr;
+    void* allreduce_ctx_ = nullptr;
+};
+
+}  // namespace agb
+
+#endif

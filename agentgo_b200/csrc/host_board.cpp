@@ -1,0 +1,184 @@
+// host_board.cpp — see host_board.h
+#include "host_board.h"
+
+#include <string.h>
+
+namespace agb {
+
+HostBoard::HostBoard(int n) { reset(n); }
+
+HostBoard::Ref HostBoard::open() const {
+    Ref r;
+    r.w0 = const_cast<uint32_t*>(pos_.w0);
+    r.w1 = const_cast<uint32_t*>(pos_.w1);
+    r.load_scalars(pos_);
+    return r;
+}
+
+void HostBoard::close(const Ref& r) { r.store_scalars(pos_); }
+
+void HostBoard::reset(int n) {
+    memset(&pos_, 0, sizeof(pos_));
+    pos_.n = (int16_t)n;
+    clear();
+}
+
+void HostBoard::clear() {
+    const int n = pos_.n;
+    memset(pos_.w0, 0, sizeof(pos_.w0));
+    memset(pos_.w1, 0, sizeof(pos_.w1));
+    Ref r = open();
+    r.n_rt = n;
+    r.clear();
+    close(r);
+}
+
+int HostBoard::play(int colour, int row, int col) {
+    const int n = pos_.n;
+    // Piece::legal, Piece.cpp:28-30
+    if ((colour != 1 && colour != 2) || row < 0 || col < 0 || row >= n || col >= n) return -1;
+    Ref r = open();
+    const int idx = row * n + col;
+    if (r.col(idx) != 0) return -2;   // reference: AG_PANIC, Board.cpp:75-78
+    r.put(colour, idx);
+    close(r);
+    return 0;
+}
+
+void HostBoard::pass(int colour) {
+    Ref r = open();
+    r.pass(colour);
+    close(r);
+}
+
+int HostBoard::replay(const uint32_t* moves, int n_moves) {
+    for (int i = 0; i < n_moves; i++) {
+        const int colour = (int)((moves[i] >> 16) & 0xff);
+        const int row = (int)((moves[i] >> 8) & 0xff), col = (int)(moves[i] & 0xff);
+        if (colour != 1 && colour != 2) return -1;
+        if (row == 0xff) { pass(colour); continue; }
+        const int st = play(colour, row, col);
+        if (st) return st;
+    }
+    return 0;
+}
+
+int HostBoard::colour_at(int idx) const { return open().col(idx); }
+
+// Board::checkNoSense, Board.cpp:883-908.  The reference has no return on the false path
+// (undefined behaviour); false is taken there.
+bool HostBoard::no_sense(int colour, int row, int col) const {
+    const Ref r = open();
+    const int n = pos_.n, enemy = 3 - colour;
+    int self1 = 0, enemy1 = 0, self2 = 0, enemy2 = 0;
+    for (int range = 1; range <= 2; range++) {
+        int s = 0, e = 0;
+        for (int i = row - range; i <= row + range; i++)
+            for (int j = col - range; j <= col + range; j++) {
+                if (i == row && j == col) continue;
+                if (i < 0 || j < 0 || i >= n || j >= n) continue;     // checkPiece, :193-198
+                const int c = r.col(i * n + j);
+                if (c == colour) s++;
+                else if (c == enemy) e++;
+            }
+        if (range == 1) { self1 = s; enemy1 = e; } else { self2 = s; enemy2 = e; }
+    }
+    const bool at_border = (row == 0 || row == n - 1 || col == 0 || col == n - 1);
+    const bool near_border = (row <= 1 || row >= n - 2 || col <= 1 || col >= n - 2);
+    return ((enemy1 + self1 == 0) && at_border) || ((enemy2 + self2 == 0) && near_border);
+}
+
+int HostBoard::check(int which, int colour, int row, int col) const {
+    const int n = pos_.n;
+    if ((colour != 1 && colour != 2) || row < 0 || col < 0 || row >= n || col >= n) return -1;
+    const Ref r = open();
+    const int idx = row * n + col;
+    const Ref::Nb q = r.scan(colour, idx);
+    switch (which) {
+        case 0: return Ref::is_suicide(q);
+        case 1: return Ref::is_kill(q);
+        case 2: return Ref::is_survive(q);
+        case 3: return Ref::is_dying(q);
+        case 4: return Ref::is_chase(q);
+        case 5: return r.true_eye(colour, idx);
+        case 6: return r.compete(colour, idx);
+        case 7: return no_sense(colour, row, col);
+    }
+    return -1;
+}
+
+int HostBoard::count_score(int colour) const { return open().count_score(colour); }
+
+bool HostBoard::is_candidate(int colour, int row, int col) const {
+    const Ref r = open();
+    const int idx = row * pos_.n + col;
+    if (r.true_eye(colour, idx)) return false;
+    if (r.col(idx) != 0) return false;
+    if (Ref::is_suicide(r.scan(colour, idx))) return false;
+    if (no_sense(colour, row, col)) return false;
+    if (r.compete(colour, idx)) return false;
+    return true;
+}
+
+bool HostBoard::is_eligible(int colour, int row, int col) const {
+    const Ref r = open();
+    const int idx = row * pos_.n + col;
+    return r.col(idx) == 0 && !r.true_eye(colour, idx) && !Ref::is_suicide(r.scan(colour, idx)) &&
+           !r.compete(colour, idx);
+}
+
+Position HostBoard::with_move(int colour, int idx) const {
+    HostBoard copy(*this);
+    Ref r = copy.open();
+    r.put(colour, idx);
+    copy.close(r);
+    return copy.pos_;
+}
+
+int HostBoard::export_state(int32_t* out, int cap) const {
+    const int n = pos_.n, NN = n * n, words = 16 + 7 * NN;
+    if (cap < words) return -1;
+    const Ref r = open();
+    memset(out, 0, sizeof(int32_t) * (size_t)words);
+    out[0] = n; out[1] = r.num_black; out[2] = r.num_white; out[3] = r.head;
+    out[4] = r.ko ? 1 : 0;
+    out[5] = r.ko ? r.ko_col : 0;
+    out[6] = r.ko ? r.ko_idx / n : -1;
+    out[7] = r.ko ? r.ko_idx % n : -1;
+    const int lm[2] = {r.last0, r.last1};
+    for (int a = 0; a < 2; a++) {
+        out[8 + 3 * a] = lm[a] >= 0 ? a + 1 : 0;
+        out[9 + 3 * a] = lm[a] >= 0 ? lm[a] / n : -1;
+        out[10 + 3 * a] = lm[a] >= 0 ? lm[a] % n : -1;
+    }
+    out[14] = r.ending ? 1 : 0;
+    int32_t* data = out + 16;
+    int32_t* root = data + NN;
+    int32_t* hp = root + NN;
+    int32_t* size = hp + NN;
+    int32_t* next = size + NN;
+    int32_t* sprev = next + NN;
+    int32_t* snext = sprev + NN;
+    for (int idx = 0; idx < NN; idx++) {
+        const int c = r.col(idx);
+        data[idx] = c;
+        if (c == 0) {
+            root[idx] = -1; next[idx] = -1;
+            sprev[idx] = r.A(idx); snext[idx] = r.B(idx);
+        } else {
+            root[idx] = r.A(idx);
+            next[idx] = r.B(idx) == kNil ? -1 : r.B(idx);
+            sprev[idx] = snext[idx] = -1;
+        }
+    }
+    for (int idx = 0; idx < NN; idx++) {
+        if (data[idx] == 0 || root[idx] != idx) continue;
+        hp[idx] = r.HP(idx);
+        int sz = 0;
+        for (int k = idx; k != kNil; k = r.B(k)) sz++;
+        size[idx] = sz;
+    }
+    return words;
+}
+
+}  // namespace agb

@@ -86,7 +86,7 @@ typedef enum agb_kernel {
 
 typedef struct agb_config {
     int board_size;      /* 9, 13 or 19 */
-    int device;          /* CUDA device ordinal */
+    int device;          /* CUDA device ordinal; -1 => position-only engine (compute calls fail) */
     int kernel;          /* agb_kernel */
     int shard_rank;      /* this engine evaluates global playout ids g with        */
     int shard_count;     /*   g % shard_count == shard_rank   (1 => everything)     */
@@ -177,6 +177,14 @@ int agb_playouts_finish(agb_engine* h, int64_t* wins, int64_t* sum_pos, int64_t*
 /* device pointer (int64[3*max(C,1)]) and CUDA stream (cudaStream_t as void*) */
 void* agb_counters_dev(agb_engine* h);
 void* agb_stream(agb_engine* h);
+
+/* Optional collective hook for sharded engines (shard_count > 1).  When set, every
+ * agb_playouts*_finish / agb_genmove step calls fn(ctx, dev_int64, count, cuda_stream)
+ * on the counters before they are copied out; fn must sum them over all shards in place
+ * (one NCCL allreduce, ncclInt64/ncclSum, enqueued on that stream or ordered after it)
+ * and return 0.  Without it a sharded engine returns its own shard's partial counts.    */
+typedef int (*agb_allreduce_fn)(void* ctx, void* dev_int64, int count, void* cuda_stream);
+int agb_set_allreduce(agb_engine* h, agb_allreduce_fn fn, void* ctx);
 
 /* batch of B independent positions (config 3): root-mode, P playouts each,
  * position b uses position_id = first_position_id + b and is evaluated by the
