@@ -29,7 +29,7 @@ SYMBOLS = [
     "agb_device_count", "agb_boardsize", "agb_clear_board", "agb_play", "agb_pass",
     "agb_get_board", "agb_check", "agb_count_score", "agb_export_state", "agb_playouts",
     "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
-    "agb_set_allreduce", "agb_playouts_batch", "agb_genmove",
+    "agb_set_allreduce", "agb_playouts_batch", "agb_genmove", "agb_measure_peaks",
 ]
 
 
@@ -111,8 +111,20 @@ def lib():
     l.agb_genmove.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64,
                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                               C.POINTER(Stats)]
+    l.agb_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _lib = l
     return l
+
+
+def measure_peaks(device=0):
+    """-> dict(int_ops_per_s, int_ops_per_s_alu_only, smem_bytes_per_s, sm_count), measured live."""
+    a, b, c, n = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+    st = lib().agb_measure_peaks(device, C.byref(a), C.byref(b), C.byref(c), C.byref(n))
+    if st:
+        raise AgbError(st, "agb_measure_peaks")
+    return {"int_ops_per_s": a.value, "int_ops_per_s_alu_only": b.value,
+            "smem_bytes_per_s": c.value, "sm_count": n.value}
 
 
 def move(colour, row, col):

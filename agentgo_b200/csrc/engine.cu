@@ -142,7 +142,6 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
         else e = launch_playout_warp(n, a, sm_count_, stream_, &info_);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     }
-    AGB_CUDA(cudaEventRecord(ev1_, stream_));
     in_flight_ = true;
     n_starts_ = S; P_ = P; want_diffs_ = want_diffs; shard_units_ = shard_units;
     return AGB_OK;
@@ -165,6 +164,8 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
         int r = allreduce_(allreduce_ctx_, d_counters_, 3 * S, (void*)stream_);
         if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
     }
+    // device time of the evaluation = kernel (+ collective), stream ordered
+    AGB_CUDA(cudaEventRecord(ev1_, stream_));
     long long* hc = (long long*)h_pinned_;
     unsigned long long* hs = (unsigned long long*)(hc + 3 * (size_t)S);
     AGB_CUDA(cudaMemcpyAsync(hc, d_counters_, sizeof(long long) * 3 * (size_t)S, cudaMemcpyDeviceToHost, stream_));

@@ -203,6 +203,13 @@ int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
 int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_root,
                 uint64_t seed_base, int* row, int* col, int* is_pass, agb_stats* stats);
 
+/* ---- diagnostics -------------------------------------------------------
+ * Live micro-benchmarks of the two rates that bound the playout kernels:
+ * INT32 lane-ops/s (mixed LOP3/IADD3/IMAD, and alu-pipe only) and conflict-free
+ * shared-memory bytes/s, at the clock the device actually sustains.              */
+int agb_measure_peaks(int device, double* int_ops_per_s, double* int_ops_per_s_alu_only,
+                      double* smem_bytes_per_s, int* sm_count);
+
 /* ---- the seed contract (shared verbatim by oracle and kernels) --------- */
 static inline uint32_t agb_playout_seed(uint64_t seed_base, uint32_t position_id,
                                         uint32_t candidate_idx, uint64_t playout_idx) {

@@ -1,0 +1,63 @@
+"""Shared helpers for the tests."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+BUILD = os.path.join(ROOT, "tests", "_build")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def split_moves(g):
+    """midgame_19.npz stores all move lists back to back."""
+    out, o = [], 0
+    for ln in g["lens"]:
+        out.append(g["moves"][o:o + int(ln)].astype(np.uint32))
+        o += int(ln)
+    return out
+
+
+def oracle_kinds(n):
+    """The oracles available on this machine: always the C port; the compiled reference when
+    oracle/_ref was built (here from /root/reference, on the GPU box from the shipped .so)."""
+    from oracle import pyoracle as po
+    kinds = ["port"]
+    if po.ref_available(n):
+        kinds.append("reference")
+    return kinds
+
+
+def host_sim():
+    """Test-only CPU harness that runs the __host__ __device__ playout logic of
+    agentgo_b200/csrc/board_ops.h (tests/csrc/host_sim.cpp)."""
+    os.makedirs(BUILD, exist_ok=True)
+    lib = os.path.join(BUILD, "libhost_sim.so")
+    srcs = [os.path.join(ROOT, "tests", "csrc", "host_sim.cpp"),
+            os.path.join(ROOT, "agentgo_b200", "csrc", "host_board.cpp")]
+    deps = srcs + [os.path.join(ROOT, "agentgo_b200", "csrc", "board_ops.h"),
+                   os.path.join(ROOT, "agentgo_b200", "csrc", "host_board.h")]
+    if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared",
+                               "-I", os.path.join(ROOT, "agentgo_b200", "csrc"),
+                               "-I", os.path.join(ROOT, "include")] + srcs + ["-o", lib])
+    return C.CDLL(lib)
+
+
+def sim_playouts(sim, n, moves, colour, cand, P, avrg_win=0, seed_base=20151001, position_id=0, cand_idx=0):
+    mv = np.ascontiguousarray(moves, dtype=np.uint32)
+    d = np.zeros(P, dtype=np.int16)
+    o = np.zeros(3, dtype=np.int64)
+    s = np.zeros(2, dtype=np.int64)
+    r = sim.sim_playouts(n, mv.ctypes.data_as(C.c_void_p), len(mv), colour,
+                         cand[0] if cand is not None else -1, cand[1] if cand is not None else -1,
+                         C.c_uint32(position_id), C.c_uint32(cand_idx), C.c_int64(P), C.c_uint64(seed_base),
+                         avrg_win, d.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
+                         s.ctypes.data_as(C.c_void_p))
+    assert r == 0
+    return o, d, s
