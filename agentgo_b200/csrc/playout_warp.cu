@@ -1,11 +1,12 @@
 // playout_warp.cu — one WARP per playout (sm_100a).
 //
-// One board (2*N*N words) per warp in shared memory, so 32+ playouts are resident per SM at
-// 19x19 (the thread-per-playout variant fits 64 but pays 32-way divergence).
+// One board (2*N*N words) per warp in shared memory, so 32 playouts are resident per SM at
+// 19x19 with 64 registers per thread (the thread-per-playout variant fits 64 boards but pays
+// 32-way divergence and has 2 warps per SM to hide latency with).
 //
-//  * State updates (put / capture / merge / pass, board_ops.h) run WARP-UNIFORM: every lane
-//    executes the same scalar code on the same shared-memory words (same address, same value),
-//    so there is no divergence and no intra-warp communication.
+//  * State updates (put / capture / merge / pass) run WARP-UNIFORM: every lane executes the
+//    same scalar code on the same shared-memory words (same address, same value), so there is
+//    no divergence and no intra-warp communication.
 //  * The policy's predicates are evaluated LANE-PARALLEL: lane = (cell, direction) with
 //    8 cells x 4 directions = 32 lanes.  In the neighbourhood phase of Board::getRandomPiece
 //    (Board.cpp:354-380) the 8 cells are the 3x3 block around the opponent's last move (its
@@ -17,6 +18,12 @@
 //    are empty the 18 draws cannot be accepted and the generator is only stepped.
 //  * Clone, scoring and the complex-mode legality pass are strided over the lanes.
 //  * The RNG (TinyMT32, one stream per playout) is warp-uniform in registers.
+//
+// The code is written for a SMALL INSTRUCTION FOOTPRINT: 32 warps per SM sit at 32 different
+// program counters, and the first version of this kernel (every helper force-inlined, both
+// movers unrolled: 6 150 SASS instructions, 98 KB) spent 70 % of its stall samples waiting for
+// instruction fetch (profiles/r01_warp_v1_*.txt).  Hence: one move loop for both colours, one
+// capture site, one complex-mode site, rolled RNG loops.
 #include "kernel_args.h"
 
 namespace agb {
@@ -25,36 +32,57 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-template <int N>
-struct WarpBoard : BoardRef<1, N> {
-    typedef BoardRef<1, N> Base;
-    int lane;
+__device__ __forceinline__ int fA(uint32_t w) { return (int)(w & 1023u); }
+__device__ __forceinline__ int fB(uint32_t w) { return (int)((w >> 10) & 1023u); }
+__device__ __forceinline__ int fCol(uint32_t w) { return (int)((w >> 20) & 3u); }
+__device__ __forceinline__ uint32_t pack0(int a, int b, int col) {
+    return (uint32_t)a | ((uint32_t)b << 10) | ((uint32_t)col << 20);
+}
 
-    struct Flags {
-        bool empty;      // cell on board and empty
-        bool kill, survive, chase;
-        bool dying, eye, suicide, ko;
-    };
+// flag bits returned by eval_cells
+enum : uint32_t {
+    F_EMPTY = 1u, F_KILL = 2u, F_SURVIVE = 4u, F_CHASE = 8u, F_BAD = 16u, F_RESERVE = 32u
+};
+
+template <int N>
+struct WarpBoard {
+    static constexpr int NN = N * N;
+    uint32_t* w0;        // A | B<<10 | colour<<20 | reserve<<22   (layout: board_ops.h)
+    uint32_t* w1;        // hp | tail<<16 at root stones
+    int lane;
+    int head;            // first empty point, -1 = none
+    int stones;          // num_black + num_white (only the sum is ever read on this path)
+    int ko_key;          // exist_compete ? compete colour<<16 | idx : -1
+    int last0, last1;    // last_move[colour-1] as idx, -1 = none
+    int ending;          // game_ending
+    TinyMT mt;
+    uint32_t draws;
+
+    __device__ __forceinline__ uint32_t rand15(const RngParams& p) {
+        mt.next_state(p.mat1, p.mat2);
+        return mt.temper(p.tmat) >> 17;
+    }
 
     // Lane-parallel evaluation of up to 8 points at once: lane = 4*cell + dir evaluates
-    // neighbour `dir` (up, left, down, right) of its cell (ci, cj).  All four lanes of a cell
-    // return the same Flags.  Equivalent to scan()/true_eye()/compete() of board_ops.h.
-    __device__ __forceinline__ Flags eval_cells(int agent, int ci, int cj) const {
+    // neighbour `dir` (up, left, down, right) of its cell (ci, cj); the four lanes of a cell
+    // return the same flags.  Restates checkSuicide/Kill/Survive/Dying/Chase/TrueEye/Compete
+    // (Board.cpp:480-755); F_BAD = dying | true eye | suicide | ko (the filter of both
+    // sampling phases), F_RESERVE = true eye | suicide | ko (complex mode, no checkDying).
+    __device__ __forceinline__ uint32_t eval_cells(int agent, int ci, int cj) const {
         const int dir = lane & 3;
         const int sh = lane & ~3;
-        const bool cell_on = ci >= 0 && ci < N && cj >= 0 && cj < N;
+        const bool cell_on = (unsigned)ci < (unsigned)N && (unsigned)cj < (unsigned)N;
         const int cidx = ci * N + cj;
-        Flags f;
-        f.empty = cell_on && Base::fCol(this->w0[cell_on ? cidx : 0]) == 0;
+        const bool empty = cell_on && fCol(w0[cell_on ? cidx : 0]) == 0;
 
         const int ni = ci + (dir == 0 ? -1 : (dir == 2 ? 1 : 0));
         const int nj = cj + (dir == 1 ? -1 : (dir == 3 ? 1 : 0));
-        const bool nb_on = cell_on && ni >= 0 && ni < N && nj >= 0 && nj < N;
-        const uint32_t wn = this->w0[nb_on ? ni * N + nj : 0];
-        const int ncol = nb_on ? Base::fCol(wn) : -1;
+        const bool nb_on = cell_on && (unsigned)ni < (unsigned)N && (unsigned)nj < (unsigned)N;
+        const uint32_t wn = w0[nb_on ? ni * N + nj : 0];
+        const int ncol = nb_on ? fCol(wn) : -1;
         const bool nb_stone = ncol > 0;
-        const int root = nb_stone ? Base::fA(wn) : -1 - dir;     // distinct negatives never match
-        const int hp = (int)(this->w1[nb_stone ? root : 0] & 0xffffu);
+        const int root = nb_stone ? fA(wn) : -1 - dir;          // distinct negatives never match
+        const int hp = (int)(w1[nb_stone ? root : 0] & 0xffffu);
 
         const int r1 = __shfl_xor_sync(kFull, root, 1);
         const int r2 = __shfl_xor_sync(kFull, root, 2);
@@ -84,122 +112,230 @@ struct WarpBoard : BoardRef<1, N> {
         const bool fcap = ((b_fcap >> sh) & 15u) != 0;
         const bool fsafe = ((b_fsafe >> sh) & 15u) != 0;
         const int tot = n_empty + fsum;
-        f.suicide = n_empty == 0 && !ecap && !fsafe;          // Board.cpp:480-524
-        f.kill = ecap;                                        // :526-563
-        f.survive = fcap && (ecap || tot > fmin);             // :565-626
-        f.dying = !ecap && tot == 1;                          // :628-679
-        f.chase = eatari && tot > 1;                          // :681-733
+        const bool suicide = n_empty == 0 && !ecap && !fsafe;       // Board.cpp:480-524
+        const bool survive = fcap && (ecap || tot > fmin);          // :565-626
+        const bool dying = !ecap && tot == 1;                       // :628-679
+        const bool chase = eatari && tot > 1;                       // :681-733
 
         // Board::checkTrueEye, :735-751 — lane `dir` also looks at one diagonal
         const unsigned b_own = __ballot_sync(kFull, !nb_on || ncol == agent);
         const int di = ci + (dir < 2 ? -1 : 1), dj = cj + ((dir & 1) ? 1 : -1);
-        const bool d_on = cell_on && di >= 0 && di < N && dj >= 0 && dj < N;
-        const int dcol = Base::fCol(this->w0[d_on ? di * N + dj : 0]);
+        const bool d_on = cell_on && (unsigned)di < (unsigned)N && (unsigned)dj < (unsigned)N;
+        const int dcol = fCol(w0[d_on ? di * N + dj : 0]);
         const unsigned b_diag = __ballot_sync(kFull, d_on && dcol == 3 - agent);
         const int cnt = __popc((b_diag >> sh) & 15u);
         const bool edge = ci == 0 || ci == N - 1 || cj == 0 || cj == N - 1;
-        f.eye = ((b_own >> sh) & 15u) == 15u && (edge ? cnt < 1 : cnt < 2);
-        f.ko = this->ko && cidx == this->ko_idx && agent == this->ko_col;   // :753-755
-        return f;
+        const bool eye = ((b_own >> sh) & 15u) == 15u && (edge ? cnt < 1 : cnt < 2);
+        const bool ko = ko_key == ((agent << 16) | cidx);           // :753-755
+        const bool reserve = eye || suicide || ko;
+        return (empty ? F_EMPTY : 0u) | (ecap ? F_KILL : 0u) | (survive ? F_SURVIVE : 0u) |
+               (chase ? F_CHASE : 0u) | ((reserve || dying) ? F_BAD : 0u) | (reserve ? F_RESERVE : 0u);
     }
 
-    // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags) is strided over
-    // the lanes (one point per lane per round); the ordered walk that maps rnd to a point
-    // follows the empty list and is warp-uniform.
-    __device__ int random_piece_complex_w(Rng& rng, int agent) {
-        constexpr int NN = N * N;
-        const int spaces = NN - this->num_black - this->num_white;
+    // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags) evaluates 8
+    // points per round with eval_cells; the ordered walk that maps rnd to a point follows the
+    // empty list and is warp-uniform.
+    __device__ __forceinline__ int random_piece_complex(const RngParams& prm, int agent) {
+        const int spaces = NN - stones;
         if (spaces == 0) return -1;
         int reserved_total = 0;
-        for (int base = 0; base < NN; base += 32) {
-            const int idx = base + lane;
-            bool res = false;
-            if (idx < NN && Base::fCol(this->w0[idx]) == 0) {
-                const typename Base::Nb q = this->scan(agent, idx);
-                res = this->true_eye(agent, idx) || Base::is_suicide(q) || this->compete(agent, idx);
-                if (res) this->w0[idx] |= (1u << 22);
-            }
-            reserved_total += __popc(__ballot_sync(kFull, res));
+#pragma unroll 1
+        for (int base = 0; base < NN; base += 8) {
+            const int idx = base + (lane >> 2);
+            const int ci = idx / N, cj = idx - ci * N;              // idx >= NN gives ci >= N: off board
+            const uint32_t f = eval_cells(agent, ci, cj);
+            const bool res = (f & F_EMPTY) && (f & F_RESERVE);
+            if (res && (lane & 3) == 0) w0[idx] |= (1u << 22);      // addReserve, :757-761
+            reserved_total += __popc(__ballot_sync(kFull, res) & 0x11111111u);
         }
         __syncwarp();
         const int range = spaces - reserved_total;
         int pick = -1;
         if (range != 0) {
-            int rnd = (int)(rng.rand15() % (uint32_t)range);
-            for (int idx = this->head;;) {
-                const uint32_t w = this->w0[idx];
+            draws++;
+            int rnd = (int)(rand15(prm) % (uint32_t)range);
+#pragma unroll 1
+            for (int idx = head;;) {
+                const uint32_t w = w0[idx];
                 if (!((w >> 22) & 1u)) {
                     if (rnd == 0) { pick = idx; break; }
                     rnd--;
                 }
-                idx = Base::fB(w);
+                idx = fB(w);
             }
         }
-        if (reserved_total) {
-            for (int idx = lane; idx < NN; idx += 32) this->w0[idx] &= ~(1u << 22);
+        if (reserved_total) {                                       // resetReserve, :764-768
+#pragma unroll 1
+            for (int idx = lane; idx < NN; idx += 32) w0[idx] &= ~(1u << 22);
             __syncwarp();
         }
         return pick;
     }
 
-    // Board::getRandomPiece, Board.cpp:341-411
-    __device__ int random_piece_w(Rng& rng, int agent) {
-        if (this->ending) {                                     // :348-351
-            if (this->num_black + this->num_white <= kEndingStones) this->ending = 0;
-            else return random_piece_complex_w(rng, agent);
+    // Board::getRandomPiece, Board.cpp:341-411; returns idx or -1 (pass)
+    __device__ __forceinline__ int random_piece(const RngParams& prm, int agent) {
+        bool complex_mode = false;
+        if (ending) {                                               // :348-351
+            if (stones <= kEndingStones) ending = 0;
+            else complex_mode = true;
         }
-        const int enemy = 3 - agent;
-        const int lm = this->last(enemy);
-        if (lm >= 0 && this->col(lm) == enemy) {                // :355-380
-            const int er = lm / N, ec = lm - er * N;
-            const int cell = lane >> 2;
-            const int cc = cell + (cell >= 4);                  // skip the (occupied) centre
-            const int ci = er - 1 + cc / 3, cj = ec - 1 + cc % 3;
-            const Flags f = eval_cells(agent, ci, cj);
-            const bool ok = f.empty && !f.dying && !f.eye && !f.suicide && !f.ko;
-            const unsigned K = __ballot_sync(kFull, ok && f.kill);
-            const unsigned S = __ballot_sync(kFull, ok && f.survive);
-            const unsigned C = __ballot_sync(kFull, ok && f.chase);
-            if ((K | S | C) == 0) {
-                // no cell can be accepted: the loop runs its 9 iterations, 2 draws each
-                rng.skip(18);
-            } else {
-                for (int k = 0; k < 9; k++) {
-                    const int a = (int)(rng.rand15() % 3u);
-                    const int b = (int)(rng.rand15() % 3u);
-                    const int c9 = a * 3 + b;
-                    if (c9 == 4) continue;                      // centre: occupied
-                    const int c8 = c9 - (c9 > 4);
-                    const unsigned m = K | (k < 6 ? S : 0u) | (k < 4 ? C : 0u);
-                    if ((m >> (4 * c8)) & 1u) return (er - 1 + a) * N + (ec - 1 + b);
+        if (!complex_mode) {
+            const int lm = agent == 1 ? last1 : last0;              // opponent's last move
+            if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
+                const int er = lm / N, ec = lm - er * N;
+                const int cell = lane >> 2;
+                const int cc = cell + (cell >= 4);                  // skip the (occupied) centre
+                const int ca = cc / 3, cb = cc - ca * 3;
+                const uint32_t f = eval_cells(agent, er - 1 + ca, ec - 1 + cb);
+                const bool ok = (f & F_EMPTY) && !(f & F_BAD);
+                const unsigned K = __ballot_sync(kFull, ok && (f & F_KILL));
+                const unsigned S = __ballot_sync(kFull, ok && (f & F_SURVIVE));
+                const unsigned C = __ballot_sync(kFull, ok && (f & F_CHASE));
+                draws += 18;
+                if ((K | S | C) == 0) {
+                    // no cell can be accepted: the loop runs its 9 iterations, 2 draws each
+#pragma unroll 2
+                    for (int i = 0; i < 18; i++) mt.next_state(prm.mat1, prm.mat2);
+                } else {
+#pragma unroll 1
+                    for (int k = 0; k < 9; k++) {
+                        const int a = (int)(rand15(prm) % 3u);
+                        const int b = (int)(rand15(prm) % 3u);
+                        const int c9 = a * 3 + b;
+                        const int c8 = c9 - (c9 > 4);
+                        const unsigned m = K | (k < 6 ? S : 0u) | (k < 4 ? C : 0u);
+                        if (c9 != 4 && ((m >> (4 * c8)) & 1u)) {    // centre (c9 == 4) is occupied
+                            draws -= 2 * (8 - k);
+                            return (er - 1 + a) * N + (ec - 1 + b);
+                        }
+                    }
+                }
+            }
+#pragma unroll 1
+            for (int count = 1;; count++) {                         // :382-406
+                draws += 2;
+                const int row = (int)(rand15(prm) % (uint32_t)N);
+                const int cl = (int)(rand15(prm) % (uint32_t)N);
+                const int idx = row * N + cl;
+                bool bad = fCol(w0[idx]) != 0;
+                if (count == kEndingThreshold) {                    // even if the 100th draw passed
+                    ending = 1;
+                    break;
+                }
+                if (!bad) {
+                    bad = (eval_cells(agent, row, cl) & F_BAD) != 0;
+                    if (!bad) return idx;
                 }
             }
         }
-        for (int count = 1;; count++) {                         // :382-406
-            const int row = (int)(rng.rand15() % (uint32_t)N);
-            const int cl = (int)(rng.rand15() % (uint32_t)N);
-            const int idx = row * N + cl;
-            bool bad = this->col(idx) != 0;
-            if (!bad) {
-                const Flags f = eval_cells(agent, row, cl);
-                bad = f.dying || f.eye || f.suicide || f.ko;
+        return random_piece_complex(prm, agent);
+    }
+
+    // Board::killSetNode, Board.cpp:293-339 (warp-uniform)
+    __device__ __forceinline__ void kill_string(int root) {
+        const bool single = (int)(w1[root] >> 16) == root;
+#pragma unroll 1
+        for (int k = root; k != kNil;) {
+            const uint32_t w = w0[k];
+            const int nx = fB(w);
+            const int agent = fCol(w);
+            stones--;
+            if (head >= 0) {                                        // push at the list head, :311-321
+                w0[k] = pack0(k, head, 0);
+                w0[head] = (w0[head] & ~1023u) | (uint32_t)k;
+            } else {
+                w0[k] = pack0(k, k, 0);
             }
-            if (count == kEndingThreshold) {                    // even if the 100th draw passed
-                this->ending = 1;
-                return random_piece_complex_w(rng, agent);
+            head = k;
+            const int i = k / N, j = k - i * N;
+#pragma unroll 1
+            for (int d = 0; d < 4; d++) {                           // one liberty back, :323-326
+                const int nb = k + (d == 0 ? -N : (d == 1 ? -1 : (d == 2 ? N : 1)));
+                const bool on = d == 0 ? i > 0 : (d == 1 ? j > 0 : (d == 2 ? i + 1 < N : j + 1 < N));
+                if (!on) continue;
+                const uint32_t v = w0[nb];
+                if (fCol(v) != 0 && fCol(v) != agent) w1[fA(v)] += 1u;
             }
-            if (!bad) return idx;
+            if (single) ko_key = (agent << 16) | k;                 // :328-333
+            k = nx;
         }
     }
 
+    // Board::put, Board.cpp:68-177 (warp-uniform; the point is empty)
+    __device__ __forceinline__ void put(int agent, int idx) {
+        const int i = idx / N, j = idx - i * N;
+        stones++;
+        ko_key = -1;
+        {                                                           // unlink from the empty list, :105-118
+            const uint32_t w = w0[idx];
+            const int sp = fA(w), sx = fB(w);
+            if (stones == NN) head = -1;
+            else if (sp == idx) { w0[sx] = (w0[sx] & ~1023u) | (uint32_t)sx; head = sx; }
+            else if (sx == idx) { w0[sp] = (w0[sp] & ~(1023u << 10)) | ((uint32_t)sp << 10); }
+            else {
+                w0[sp] = (w0[sp] & ~(1023u << 10)) | ((uint32_t)sx << 10);
+                w0[sx] = (w0[sx] & ~1023u) | (uint32_t)sp;
+            }
+        }
+        w0[idx] = pack0(idx, kNil, agent);                          // SetNode::init, SetNode.cpp:31-44
+        w1[idx] = (uint32_t)idx << 16;
+        int hp_self = 0;                                            // own liberties before captures, :123-127
+#pragma unroll 1
+        for (int d = 0; d < 4; d++) {
+            const int nb = idx + (d == 0 ? -N : (d == 1 ? -1 : (d == 2 ? N : 1)));
+            const bool on = d == 0 ? i > 0 : (d == 1 ? j > 0 : (d == 2 ? i + 1 < N : j + 1 < N));
+            if (on && fCol(w0[nb]) == 0) hp_self++;
+        }
+        // up, left, down, right (:129-164), then the stone's own string (:165-167) as step 4
+#pragma unroll 1
+        for (int d = 0; d < 5; d++) {
+            int victim = -1;
+            if (d < 4) {
+                const int nb = idx + (d == 0 ? -N : (d == 1 ? -1 : (d == 2 ? N : 1)));
+                const bool on = d == 0 ? i > 0 : (d == 1 ? j > 0 : (d == 2 ? i + 1 < N : j + 1 < N));
+                if (!on) continue;
+                const uint32_t v = w0[nb];
+                if (fCol(v) == 0) continue;
+                const int sn = fA(v);
+                const uint32_t h = w1[sn] - 1u;                     // sn->hp -= 1
+                w1[sn] = h;
+                if (fCol(v) != agent) {
+                    if ((h & 0xffffu) == 0) victim = sn;
+                } else {
+                    // Board::unionSetNode(sn, getSet(idx)), :279-291: sn survives, its stones first
+                    const int s2 = fA(w0[idx]);
+                    if (s2 != sn) {
+                        const uint32_t h2 = w1[s2];
+                        const int t1 = (int)(h >> 16);
+                        w1[sn] = ((h + h2) & 0xffffu) | (h2 & 0xffff0000u);
+                        w0[t1] = (w0[t1] & ~(1023u << 10)) | ((uint32_t)s2 << 10);
+#pragma unroll 1
+                        for (int k = s2; k != kNil;) {
+                            const uint32_t w = w0[k];
+                            w0[k] = (w & ~1023u) | (uint32_t)sn;
+                            k = fB(w);
+                        }
+                    }
+                }
+            } else {
+                const int self = fA(w0[idx]);
+                const uint32_t h = w1[self] + (uint32_t)hp_self;
+                w1[self] = h;
+                if ((h & 0xffffu) == 0) victim = self;
+            }
+            if (victim >= 0) kill_string(victim);
+        }
+        if (agent == 1) last0 = idx; else last1 = idx;             // :171
+    }
+
     // Board::countScore(agent) - countScore(enemy), Board.cpp:910-925, strided over the lanes
-    __device__ int score_diff(int agent) const {
-        constexpr int NN = N * N;
+    __device__ __forceinline__ int score_diff(int agent) const {
         int d = 0;
+#pragma unroll 1
         for (int idx = lane; idx < NN; idx += 32) {
             const int i = idx / N, j = idx - i * N;
-            const int c = Base::fCol(this->w0[idx]);
-            const int owner = c != 0 ? c : Base::fCol(this->w0[j > 0 ? idx - 1 : idx + 1]);
+            const int c = fCol(w0[idx]);
+            const int owner = c != 0 ? c : fCol(w0[j > 0 ? idx - 1 : idx + 1]);
             d += (owner == agent) - (owner == 3 - agent);
         }
 #pragma unroll
@@ -220,12 +356,12 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
     WarpBoard<N> bd;
     bd.w0 = smem + (size_t)warp * BoardWords<N>::value;
     bd.w1 = bd.w0 + NN;
-    bd.n_rt = N;
     bd.lane = lane;
 
     unsigned long long moves = 0, draws = 0;
     unsigned int faults = 0, played = 0;
 
+#pragma unroll 1
     for (;;) {
         unsigned long long l = 0;
         if (lane == 0) l = atomicAdd(a.work_counter, 1ull);
@@ -238,41 +374,66 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         const StartDesc d = a.descs[s];
 
         __syncwarp();
-        for (int i = lane; i < NN; i += 32) {                   // Board::clone, Board.cpp:216-254
+#pragma unroll 1
+        for (int i = lane; i < NN; i += 32) {                       // Board::clone, Board.cpp:216-254
             bd.w0[i] = pos.w0[i];
             bd.w1[i] = pos.w1[i];
         }
-        bd.load_scalars(pos);
+        bd.head = pos.head;
+        bd.stones = pos.num_black + pos.num_white;
+        bd.ko_key = pos.ko ? ((pos.ko_col << 16) | pos.ko_idx) : -1;
+        bd.last0 = pos.last[0];
+        bd.last1 = pos.last[1];
+        bd.ending = pos.ending;
+        bd.draws = 0;
         __syncwarp();
+        {
+            // tinymt32_init (RFC 8682), rolled
+            uint32_t st[4] = {playout_seed(a.seed_base, d.position_id, d.cand_idx, (uint64_t)p),
+                              a.rng.mat1, a.rng.mat2, a.rng.tmat};
+#pragma unroll
+            for (int i = 1; i < 8; i++)
+                st[i & 3] ^= (uint32_t)i + 1812433253u * (st[(i - 1) & 3] ^ (st[(i - 1) & 3] >> 30));
+            if ((st[0] & 0x7fffffffu) == 0 && st[1] == 0 && st[2] == 0 && st[3] == 0) {
+                st[0] = 'T'; st[1] = 'I'; st[2] = 'N'; st[3] = 'Y';
+            }
+            bd.mt.s0 = st[0]; bd.mt.s1 = st[1]; bd.mt.s2 = st[2]; bd.mt.s3 = st[3];
+#pragma unroll 1
+            for (int i = 0; i < 8; i++) bd.mt.next_state(a.rng.mat1, a.rng.mat2);
+        }
 
-        Rng rng;
-        rng.seed(playout_seed(a.seed_base, d.position_id, d.cand_idx, (uint64_t)p), a.rng);
-
-        // pair loop of MyWorker::work (AgentGo.cpp:295-325) / testAvrgWin (:422-443)
-        const int first = d.first, second = 3 - d.first;
-        bool go1 = true, go2 = true, fault = false;
+        // pair loop of MyWorker::work (AgentGo.cpp:295-325) / testAvrgWin (:422-443), one move
+        // per iteration: the loop ends after a pair in which neither side moved.
+        const int first = d.first;
+        bool first_moved = true, fault = false;
         uint32_t mv = 0;
-        while (go1 || go2) {
-            int r = bd.random_piece_w(rng, first);
-            if (r >= 0) { bd.put(first, r); go1 = true; mv++; }
-            else { go1 = false; bd.pass(first); }
-            r = bd.random_piece_w(rng, second);
-            if (r >= 0) { bd.put(second, r); go2 = true; mv++; }
-            else { go2 = false; bd.pass(second); }
+#pragma unroll 1
+        for (int t = 0;; t++) {
+            const int colour = (t & 1) ? 3 - first : first;
+            const int r = bd.random_piece(a.rng, colour);
+            if (r >= 0) {
+                bd.put(colour, r);
+                mv++;
+            } else {                                                // Board::pass, Board.cpp:200-203
+                bd.ko_key = -1;
+                if (colour == 1) bd.last0 = -1; else bd.last1 = -1;
+            }
+            if (!(t & 1)) first_moved = r >= 0;
+            else if (!first_moved && r < 0) break;
             if ((int)mv > a.max_moves) { fault = true; break; }
         }
         __syncwarp();
         const int diff = fault ? -32768 : bd.score_diff(d.agent);
         moves += mv;
-        draws += rng.draws;
+        draws += bd.draws;
         played++;
         if (fault) faults++;
         if (lane == 0) {
             if (a.diffs) a.diffs[g] = (int16_t)diff;
             if (!fault) {
-                const int w = diff - d.avrg_win;                 // AgentGo.cpp:327
+                const int w = diff - d.avrg_win;                     // AgentGo.cpp:327
                 unsigned long long* c = (unsigned long long*)a.counters;
-                if (w >= 0) {                                    // sign test of AgentGo.cpp:328
+                if (w >= 0) {                                        // sign test of AgentGo.cpp:328
                     atomicAdd(&c[s], 1ull);
                     atomicAdd(&c[a.n_starts + s], (unsigned long long)w);
                 } else {
