@@ -49,6 +49,7 @@ struct WarpBoard {
     static constexpr int NN = N * N;
     uint32_t* w0;        // A | B<<10 | colour<<20 | reserve<<22   (layout: board_ops.h)
     uint32_t* w1;        // hp | tail<<16 at root stones
+    uint16_t* scratch;   // NN entries: compacted list of empty points (complex mode)
     int lane;
     int head;            // first empty point, -1 = none
     int stones;          // num_black + num_white (only the sum is ever read on this path)
@@ -132,19 +133,31 @@ struct WarpBoard {
                (chase ? F_CHASE : 0u) | ((reserve || dying) ? F_BAD : 0u) | (reserve ? F_RESERVE : 0u);
     }
 
-    // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags) evaluates 8
-    // points per round with eval_cells; the ordered walk that maps rnd to a point follows the
-    // empty list and is warp-uniform.
+    // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags): the empty points
+    // are compacted with ballots, then evaluated 8 per round with eval_cells; the ordered walk
+    // that maps rnd to a point follows the empty list and is warp-uniform.
     __device__ __forceinline__ int random_piece_complex(const RngParams& prm, int agent) {
         const int spaces = NN - stones;
         if (spaces == 0) return -1;
+        // compact the empty points (index order) so that pass 1 only evaluates those
+        int n_e = 0;
+#pragma unroll 1
+        for (int base = 0; base < NN; base += 32) {
+            const int idx = base + lane;
+            const bool e = idx < NN && fCol(w0[idx]) == 0;
+            const unsigned m = __ballot_sync(kFull, e);
+            if (e) scratch[n_e + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
+            n_e += __popc(m);
+        }
+        __syncwarp();
         int reserved_total = 0;
 #pragma unroll 1
-        for (int base = 0; base < NN; base += 8) {
-            const int idx = base + (lane >> 2);
-            const int ci = idx / N, cj = idx - ci * N;              // idx >= NN gives ci >= N: off board
+        for (int base = 0; base < n_e; base += 8) {
+            const int k = base + (lane >> 2);
+            const int idx = k < n_e ? (int)scratch[k] : -1;         // -1 decodes to an off-board cell
+            const int ci = idx / N, cj = idx - ci * N;
             const uint32_t f = eval_cells(agent, ci, cj);
-            const bool res = (f & F_EMPTY) && (f & F_RESERVE);
+            const bool res = idx >= 0 && (f & F_RESERVE);
             if (res && (lane & 3) == 0) w0[idx] |= (1u << 22);      // addReserve, :757-761
             reserved_total += __popc(__ballot_sync(kFull, res) & 0x11111111u);
         }
@@ -279,23 +292,24 @@ struct WarpBoard {
         }
         w0[idx] = pack0(idx, kNil, agent);                          // SetNode::init, SetNode.cpp:31-44
         w1[idx] = (uint32_t)idx << 16;
-        int hp_self = 0;                                            // own liberties before captures, :123-127
-#pragma unroll 1
-        for (int d = 0; d < 4; d++) {
-            const int nb = idx + (d == 0 ? -N : (d == 1 ? -1 : (d == 2 ? N : 1)));
-            const bool on = d == 0 ? i > 0 : (d == 1 ? j > 0 : (d == 2 ? i + 1 < N : j + 1 < N));
-            if (on && fCol(w0[nb]) == 0) hp_self++;
-        }
+        // lane d (mod 4) looks at neighbour d (up, left, down, right) once: own liberties before
+        // any capture (:123-127) and the set of directions that hold a stone
+        const int dl = lane & 3;
+        const int nb_l = idx + (dl == 0 ? -N : (dl == 1 ? -1 : (dl == 2 ? N : 1)));
+        const bool on_l = dl == 0 ? i > 0 : (dl == 1 ? j > 0 : (dl == 2 ? i + 1 < N : j + 1 < N));
+        const int col_l = on_l ? fCol(w0[nb_l]) : -1;
+        const int hp_self = __popc(__ballot_sync(kFull, col_l == 0) & 15u);
+        unsigned todo = (__ballot_sync(kFull, col_l > 0) & 15u) | 16u;
         // up, left, down, right (:129-164), then the stone's own string (:165-167) as step 4
 #pragma unroll 1
-        for (int d = 0; d < 5; d++) {
+        while (todo) {
+            const int d = __ffs(todo) - 1;
+            todo &= todo - 1;
             int victim = -1;
             if (d < 4) {
-                const int nb = idx + (d == 0 ? -N : (d == 1 ? -1 : (d == 2 ? N : 1)));
-                const bool on = d == 0 ? i > 0 : (d == 1 ? j > 0 : (d == 2 ? i + 1 < N : j + 1 < N));
-                if (!on) continue;
+                const int nb = __shfl_sync(kFull, nb_l, d);
                 const uint32_t v = w0[nb];
-                if (fCol(v) == 0) continue;
+                if (fCol(v) == 0) continue;                         // captured earlier in this put
                 const int sn = fA(v);
                 const uint32_t h = w1[sn] - 1u;                     // sn->hp -= 1
                 w1[sn] = h;
@@ -344,8 +358,9 @@ struct WarpBoard {
     }
 };
 
+// per-warp shared memory: w0[NN], w1[NN], scratch[NN] (16 bit), rounded to 32 words
 template <int N>
-struct BoardWords { static constexpr int value = ((2 * N * N + 31) / 32) * 32; };
+struct BoardWords { static constexpr int value = ((2 * N * N + (N * N + 1) / 2 + 31) / 32) * 32; };
 
 template <int N, int WARPS, int BLOCKS_PER_SM>
 __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel(const KernelArgs a) {
@@ -356,6 +371,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
     WarpBoard<N> bd;
     bd.w0 = smem + (size_t)warp * BoardWords<N>::value;
     bd.w1 = bd.w0 + NN;
+    bd.scratch = reinterpret_cast<uint16_t*>(bd.w1 + NN);
     bd.lane = lane;
 
     unsigned long long moves = 0, draws = 0;
