@@ -70,6 +70,19 @@ int Engine::create(const agb_config& cfg, Engine** out, std::string* err) {
         return AGB_ERR_CUDA;
     }
     h->sm_count_ = prop.multiProcessorCount;
+    {
+        JumpTable* jt = new JumpTable;
+        RngParams prm = {h->cfg.mat1, h->cfg.mat2, h->cfg.tmat};
+        build_jump18(prm, jt);
+        e = cudaMalloc(&h->d_jump_, sizeof(JumpTable));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_jump_, jt, sizeof(JumpTable), cudaMemcpyHostToDevice);
+        delete jt;
+        if (e != cudaSuccess) {
+            if (err) *err = std::string("CUDA init (jump table): ") + cudaGetErrorString(e);
+            delete h;
+            return AGB_ERR_CUDA;
+        }
+    }
     *out = h;
     return AGB_OK;
 }
@@ -79,7 +92,7 @@ Engine::~Engine() {
     cudaSetDevice(cfg.device);
     if (stream_) cudaStreamSynchronize(stream_);
     cudaFree(d_starts_); cudaFree(d_descs_); cudaFree(d_counters_); cudaFree(d_diffs_);
-    cudaFree(d_small_);
+    cudaFree(d_small_); cudaFree(d_jump_);
     if (h_pinned_) cudaFreeHost(h_pinned_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -106,12 +119,20 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     AGB_CUDA(cudaSetDevice(cfg.device));
     const int S = (int)starts.size();
     int st;
-    if ((st = ensure(&d_starts_, &cap_starts_, sizeof(Position) * (size_t)S))) return st;
+    const bool thread_kernel = cfg.kernel == AGB_KERNEL_THREAD;
+    const size_t start_bytes = (thread_kernel ? sizeof(Position) : sizeof(PaddedPosition)) * (size_t)S;
+    if ((st = ensure(&d_starts_, &cap_starts_, start_bytes))) return st;
     if ((st = ensure(&d_descs_, &cap_descs_, sizeof(StartDesc) * (size_t)S))) return st;
     if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)S))) return st;
     if (want_diffs && (st = ensure(&d_diffs_, &cap_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P))) return st;
 
-    AGB_CUDA(cudaMemcpyAsync(d_starts_, starts.data(), sizeof(Position) * (size_t)S, cudaMemcpyHostToDevice, stream_));
+    const void* start_src = starts.data();
+    if (!thread_kernel) {
+        padded_.resize(S);
+        for (int i = 0; i < S; i++) to_padded(starts[i], &padded_[i]);
+        start_src = padded_.data();
+    }
+    AGB_CUDA(cudaMemcpyAsync(d_starts_, start_src, start_bytes, cudaMemcpyHostToDevice, stream_));
     AGB_CUDA(cudaMemcpyAsync(d_descs_, descs.data(), sizeof(StartDesc) * (size_t)S, cudaMemcpyHostToDevice, stream_));
     AGB_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(long long) * 3 * (size_t)S, stream_));
     AGB_CUDA(cudaMemsetAsync(d_small_, 0, kSmallWords * sizeof(unsigned long long), stream_));
@@ -119,6 +140,8 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     KernelArgs a;
     memset(&a, 0, sizeof(a));
     a.starts = (const Position*)d_starts_;
+    a.pstarts = (const PaddedPosition*)d_starts_;
+    a.jump18 = (const JumpTable*)d_jump_;
     a.descs = (const StartDesc*)d_descs_;
     a.n_starts = S;
     a.P = P;
@@ -138,7 +161,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     if (a.local_units > 0) {
         cudaError_t e;
         const int n = board.n();
-        if (cfg.kernel == AGB_KERNEL_THREAD) e = launch_playout_thread(n, a, sm_count_, stream_, &info_);
+        if (thread_kernel) e = launch_playout_thread(n, a, sm_count_, stream_, &info_);
         else e = launch_playout_warp(n, a, sm_count_, stream_, &info_);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     }

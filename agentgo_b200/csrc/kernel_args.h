@@ -9,12 +9,33 @@
 
 namespace agb {
 
+// Device layout of a start position for the warp kernel: the board is padded to (N+2)x(N+2)
+// with a border of colour 3, so no neighbour access needs a bounds check.  Every index stored
+// in the state (links, roots, tails, head, last moves, ko point) is a padded index
+// p = (row+1)*(N+2) + (col+1).
+constexpr int kMaxW = kMaxN + 2;
+constexpr int kMaxNP = kMaxW * kMaxW;
+struct PaddedPosition {
+    uint32_t w0[kMaxNP];
+    uint32_t w1[kMaxNP];
+    int16_t head, stones, ko_key_col, ko_idx, last[2], ending, pad;
+};
+
+// GF(2) jump-ahead table of TinyMT32: T^18 split by state nibble.  jump[l*16 + v] is the image
+// of state nibble l (bits 4l..4l+3 of s0|s1|s2|s3) having value v; the new state is the XOR of
+// the 32 selected entries.
+struct JumpTable {
+    uint4 e[32 * 16];
+};
+
 // One launch evaluates `n_starts` start positions x P playouts each.  Unit of work: global
 // playout id g = start*P + p; this engine runs the ids with g % shard_count == shard_rank.
 // Units are handed out dynamically from `work_counter` (playout length varies 360..600 moves
 // at 19x19), which cannot change results: the seed is a pure function of (start, p).
 struct KernelArgs {
-    const Position* starts;     // [n_starts] device
+    const Position* starts;     // [n_starts] device (thread kernel)
+    const PaddedPosition* pstarts;  // [n_starts] device (warp kernel)
+    const JumpTable* jump18;    // device
     const StartDesc* descs;     // [n_starts] device
     int32_t n_starts;
     int64_t P;
@@ -36,6 +57,10 @@ struct LaunchInfo {
     size_t smem;
     const char* name;
 };
+
+// host helpers of the warp kernel's device layout (playout_warp.cu)
+void to_padded(const Position& p, PaddedPosition* out);
+void build_jump18(const RngParams& prm, JumpTable* out);
 
 // thread-per-playout kernel (playout_thread.cu)
 cudaError_t launch_playout_thread(int n, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info);

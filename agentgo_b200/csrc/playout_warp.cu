@@ -1,9 +1,12 @@
 // playout_warp.cu — one WARP per playout (sm_100a).
 //
-// One board (2*N*N words) per warp in shared memory, so 32 playouts are resident per SM at
-// 19x19 with 64 registers per thread (the thread-per-playout variant fits 64 boards but pays
-// 32-way divergence and has 2 warps per SM to hide latency with).
+// One board per warp in shared memory, so 32 playouts are resident per SM at 19x19 with 64
+// registers per thread (the thread-per-playout variant fits 64 boards but pays 32-way
+// divergence and has 2 warps per SM to hide latency with).
 //
+//  * The board is padded to (N+2)x(N+2) with a border of colour 3 (PaddedPosition,
+//    kernel_args.h): neighbour and diagonal reads need no bounds checks, and every stored index
+//    (links, roots, tails, head, last moves, ko point) is a padded index.
 //  * State updates (put / capture / merge / pass) run WARP-UNIFORM: every lane executes the
 //    same scalar code on the same shared-memory words (same address, same value), so there is
 //    no divergence and no intra-warp communication.
@@ -14,16 +17,21 @@
 //    (kill / survive / chase, already filtered by dying / true eye / suicide / ko).  The
 //    reference's 9-iteration loop then degenerates to two RNG draws + a bit test per
 //    iteration, consuming exactly the reference's draw sequence (the predicates are pure
-//    functions of the state, which does not change inside the loop).  When all three masks
-//    are empty the 18 draws cannot be accepted and the generator is only stepped.
-//  * Clone, scoring and the complex-mode legality pass are strided over the lanes.
+//    functions of the state, which does not change inside the loop).
+//  * When all three masks are empty (75 % of the moves) none of the 18 draws can be accepted;
+//    the generator is advanced by 18 steps at once: TinyMT32's transition is linear over GF(2),
+//    so T^18 is applied as 32 per-lane nibble-table lookups (one LDG.128 per lane) folded by
+//    four redux.xor — about a dozen instructions instead of 18 x 12.
+//  * Clone, scoring and the complex-mode legality pass are strided over the lanes; complex mode
+//    first compacts the empty points with ballots.
 //  * The RNG (TinyMT32, one stream per playout) is warp-uniform in registers.
 //
 // The code is written for a SMALL INSTRUCTION FOOTPRINT: 32 warps per SM sit at 32 different
 // program counters, and the first version of this kernel (every helper force-inlined, both
 // movers unrolled: 6 150 SASS instructions, 98 KB) spent 70 % of its stall samples waiting for
 // instruction fetch (profiles/r01_warp_v1_*.txt).  Hence: one move loop for both colours, one
-// capture site, one complex-mode site, rolled RNG loops.
+// capture site, one complex-mode site, rolled loops.  Since then the kernel is bound by the
+// integer ALU pipe (profiles/r01_warp_v3_*.txt), so the remaining lever is instruction count.
 #include "kernel_args.h"
 
 namespace agb {
@@ -31,10 +39,12 @@ namespace agb {
 namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kBorder = 3;
 
 __device__ __forceinline__ int fA(uint32_t w) { return (int)(w & 1023u); }
 __device__ __forceinline__ int fB(uint32_t w) { return (int)((w >> 10) & 1023u); }
 __device__ __forceinline__ int fCol(uint32_t w) { return (int)((w >> 20) & 3u); }
+__device__ __forceinline__ bool is_stone(int col) { return ((col + 1) & 2) != 0; }   // 1 or 2
 __device__ __forceinline__ uint32_t pack0(int a, int b, int col) {
     return (uint32_t)a | ((uint32_t)b << 10) | ((uint32_t)col << 20);
 }
@@ -46,11 +56,16 @@ enum : uint32_t {
 
 template <int N>
 struct WarpBoard {
+    static constexpr int W = N + 2;
+    static constexpr int NP = W * W;
     static constexpr int NN = N * N;
-    uint32_t* w0;        // A | B<<10 | colour<<20 | reserve<<22   (layout: board_ops.h)
+    uint32_t* w0;        // A | B<<10 | colour<<20 | reserve<<22   (field meaning: board_ops.h)
     uint32_t* w1;        // hp | tail<<16 at root stones
     uint16_t* scratch;   // NN entries: compacted list of empty points (complex mode)
     int lane;
+    int off_nb;          // offset of this lane's orthogonal neighbour (dir = lane & 3: up, left, down, right)
+    int off_dg;          // offset of this lane's diagonal
+    int off_cell;        // offset of this lane's cell in the 3x3 block around a point (cell = lane >> 2)
     int head;            // first empty point, -1 = none
     int stones;          // num_black + num_white (only the sum is ever read on this path)
     int ko_key;          // exist_compete ? compete colour<<16 | idx : -1
@@ -59,30 +74,47 @@ struct WarpBoard {
     TinyMT mt;
     uint32_t draws;
 
+    __device__ __forceinline__ void init_lane(int l) {
+        lane = l;
+        const int dir = l & 3;
+        off_nb = dir == 0 ? -W : (dir == 1 ? -1 : (dir == 2 ? W : 1));
+        off_dg = (dir < 2 ? -W : W) + ((dir & 1) ? 1 : -1);
+        const int cell = l >> 2;
+        const int cc = cell + (cell >= 4);                          // skip the centre of the 3x3 block
+        off_cell = (cc / 3 - 1) * W + (cc % 3 - 1);
+    }
+
     __device__ __forceinline__ uint32_t rand15(const RngParams& p) {
         mt.next_state(p.mat1, p.mat2);
         return mt.temper(p.tmat) >> 17;
     }
 
+    // advance the generator by 18 steps (values not needed): s' = T^18 s over GF(2)
+    __device__ __forceinline__ void jump18(const JumpTable* __restrict__ jt) {
+        const uint32_t word = lane < 16 ? (lane < 8 ? mt.s0 : mt.s1) : (lane < 24 ? mt.s2 : mt.s3);
+        const uint32_t nib = (word >> ((lane & 7) * 4)) & 15u;
+        const uint4 t = __ldg(&jt->e[lane * 16 + nib]);
+        mt.s0 = __reduce_xor_sync(kFull, t.x);
+        mt.s1 = __reduce_xor_sync(kFull, t.y);
+        mt.s2 = __reduce_xor_sync(kFull, t.z);
+        mt.s3 = __reduce_xor_sync(kFull, t.w);
+    }
+
     // Lane-parallel evaluation of up to 8 points at once: lane = 4*cell + dir evaluates
-    // neighbour `dir` (up, left, down, right) of its cell (ci, cj); the four lanes of a cell
-    // return the same flags.  Restates checkSuicide/Kill/Survive/Dying/Chase/TrueEye/Compete
-    // (Board.cpp:480-755); F_BAD = dying | true eye | suicide | ko (the filter of both
-    // sampling phases), F_RESERVE = true eye | suicide | ko (complex mode, no checkDying).
-    __device__ __forceinline__ uint32_t eval_cells(int agent, int ci, int cj) const {
+    // neighbour `dir` (up, left, down, right) of its cell `cidx` (padded index; a border cell
+    // yields no F_EMPTY); the four lanes of a cell return the same flags.  Restates
+    // checkSuicide/Kill/Survive/Dying/Chase/TrueEye/Compete (Board.cpp:480-755);
+    // F_BAD = dying | true eye | suicide | ko (the filter of both sampling phases),
+    // F_RESERVE = true eye | suicide | ko (complex mode, no checkDying).
+    __device__ __forceinline__ uint32_t eval_cells(int agent, int cidx) const {
         const int dir = lane & 3;
         const int sh = lane & ~3;
-        const bool cell_on = (unsigned)ci < (unsigned)N && (unsigned)cj < (unsigned)N;
-        const int cidx = ci * N + cj;
-        const bool empty = cell_on && fCol(w0[cell_on ? cidx : 0]) == 0;
-
-        const int ni = ci + (dir == 0 ? -1 : (dir == 2 ? 1 : 0));
-        const int nj = cj + (dir == 1 ? -1 : (dir == 3 ? 1 : 0));
-        const bool nb_on = cell_on && (unsigned)ni < (unsigned)N && (unsigned)nj < (unsigned)N;
-        const uint32_t wn = w0[nb_on ? ni * N + nj : 0];
-        const int ncol = nb_on ? fCol(wn) : -1;
-        const bool nb_stone = ncol > 0;
-        const int root = nb_stone ? fA(wn) : -1 - dir;          // distinct negatives never match
+        const int ccol = fCol(w0[cidx]);
+        const bool cell_on = ccol != kBorder;
+        const uint32_t wn = w0[cell_on ? cidx + off_nb : 0];        // w0[0] is a border cell
+        const int ncol = fCol(wn);
+        const bool nb_stone = is_stone(ncol);
+        const int root = nb_stone ? fA(wn) : -1 - dir;              // distinct negatives never match
         const int hp = (int)(w1[nb_stone ? root : 0] & 0xffffu);
 
         const int r1 = __shfl_xor_sync(kFull, root, 1);
@@ -92,8 +124,8 @@ struct WarpBoard {
         const bool first = !((r1 == root && (dir ^ 1) < dir) || (r2 == root && (dir ^ 2) < dir) ||
                              (r3 == root && (dir ^ 3) < dir));
         const int left = hp - mult;
-        const bool enemy = nb_stone && ncol != agent;
-        const bool frnd = nb_stone && ncol == agent;
+        const bool enemy = ncol == 3 - agent;
+        const bool frnd = ncol == agent;
 
         const unsigned b_empty = __ballot_sync(kFull, ncol == 0);
         const unsigned b_ecap = __ballot_sync(kFull, enemy && left == 0);
@@ -118,18 +150,18 @@ struct WarpBoard {
         const bool dying = !ecap && tot == 1;                       // :628-679
         const bool chase = eatari && tot > 1;                       // :681-733
 
-        // Board::checkTrueEye, :735-751 — lane `dir` also looks at one diagonal
-        const unsigned b_own = __ballot_sync(kFull, !nb_on || ncol == agent);
-        const int di = ci + (dir < 2 ? -1 : 1), dj = cj + ((dir & 1) ? 1 : -1);
-        const bool d_on = cell_on && (unsigned)di < (unsigned)N && (unsigned)dj < (unsigned)N;
-        const int dcol = fCol(w0[d_on ? di * N + dj : 0]);
-        const unsigned b_diag = __ballot_sync(kFull, d_on && dcol == 3 - agent);
+        // Board::checkTrueEye, :735-751 — lane `dir` also looks at one diagonal; a cell is on the
+        // edge iff one of its orthogonal neighbours is a border cell
+        const unsigned b_off = __ballot_sync(kFull, ncol == kBorder);
+        const unsigned b_own = __ballot_sync(kFull, ncol == kBorder || ncol == agent);
+        const int dcol = fCol(w0[cell_on ? cidx + off_dg : 0]);
+        const unsigned b_diag = __ballot_sync(kFull, dcol == 3 - agent);
         const int cnt = __popc((b_diag >> sh) & 15u);
-        const bool edge = ci == 0 || ci == N - 1 || cj == 0 || cj == N - 1;
-        const bool eye = ((b_own >> sh) & 15u) == 15u && (edge ? cnt < 1 : cnt < 2);
+        const bool edge = ((b_off >> sh) & 15u) != 0;
+        const bool eye = ((b_own >> sh) & 15u) == 15u && cnt < (edge ? 1 : 2);
         const bool ko = ko_key == ((agent << 16) | cidx);           // :753-755
         const bool reserve = eye || suicide || ko;
-        return (empty ? F_EMPTY : 0u) | (ecap ? F_KILL : 0u) | (survive ? F_SURVIVE : 0u) |
+        return (ccol == 0 ? F_EMPTY : 0u) | (ecap ? F_KILL : 0u) | (survive ? F_SURVIVE : 0u) |
                (chase ? F_CHASE : 0u) | ((reserve || dying) ? F_BAD : 0u) | (reserve ? F_RESERVE : 0u);
     }
 
@@ -139,12 +171,11 @@ struct WarpBoard {
     __device__ __forceinline__ int random_piece_complex(const RngParams& prm, int agent) {
         const int spaces = NN - stones;
         if (spaces == 0) return -1;
-        // compact the empty points (index order) so that pass 1 only evaluates those
         int n_e = 0;
 #pragma unroll 1
-        for (int base = 0; base < NN; base += 32) {
+        for (int base = 0; base < NP; base += 32) {
             const int idx = base + lane;
-            const bool e = idx < NN && fCol(w0[idx]) == 0;
+            const bool e = idx < NP && fCol(w0[idx]) == 0;
             const unsigned m = __ballot_sync(kFull, e);
             if (e) scratch[n_e + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
             n_e += __popc(m);
@@ -154,10 +185,9 @@ struct WarpBoard {
 #pragma unroll 1
         for (int base = 0; base < n_e; base += 8) {
             const int k = base + (lane >> 2);
-            const int idx = k < n_e ? (int)scratch[k] : -1;         // -1 decodes to an off-board cell
-            const int ci = idx / N, cj = idx - ci * N;
-            const uint32_t f = eval_cells(agent, ci, cj);
-            const bool res = idx >= 0 && (f & F_RESERVE);
+            const int idx = k < n_e ? (int)scratch[k] : 0;          // 0 is a border cell
+            const uint32_t f = eval_cells(agent, idx);
+            const bool res = (f & F_EMPTY) && (f & F_RESERVE);
             if (res && (lane & 3) == 0) w0[idx] |= (1u << 22);      // addReserve, :757-761
             reserved_total += __popc(__ballot_sync(kFull, res) & 0x11111111u);
         }
@@ -179,14 +209,14 @@ struct WarpBoard {
         }
         if (reserved_total) {                                       // resetReserve, :764-768
 #pragma unroll 1
-            for (int idx = lane; idx < NN; idx += 32) w0[idx] &= ~(1u << 22);
+            for (int k = lane; k < n_e; k += 32) w0[scratch[k]] &= ~(1u << 22);
             __syncwarp();
         }
         return pick;
     }
 
-    // Board::getRandomPiece, Board.cpp:341-411; returns idx or -1 (pass)
-    __device__ __forceinline__ int random_piece(const RngParams& prm, int agent) {
+    // Board::getRandomPiece, Board.cpp:341-411; returns the (padded) point or -1 (pass)
+    __device__ __forceinline__ int random_piece(const RngParams& prm, const JumpTable* jt, int agent) {
         bool complex_mode = false;
         if (ending) {                                               // :348-351
             if (stones <= kEndingStones) ending = 0;
@@ -195,11 +225,7 @@ struct WarpBoard {
         if (!complex_mode) {
             const int lm = agent == 1 ? last1 : last0;              // opponent's last move
             if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
-                const int er = lm / N, ec = lm - er * N;
-                const int cell = lane >> 2;
-                const int cc = cell + (cell >= 4);                  // skip the (occupied) centre
-                const int ca = cc / 3, cb = cc - ca * 3;
-                const uint32_t f = eval_cells(agent, er - 1 + ca, ec - 1 + cb);
+                const uint32_t f = eval_cells(agent, lm + off_cell);
                 const bool ok = (f & F_EMPTY) && !(f & F_BAD);
                 const unsigned K = __ballot_sync(kFull, ok && (f & F_KILL));
                 const unsigned S = __ballot_sync(kFull, ok && (f & F_SURVIVE));
@@ -207,8 +233,7 @@ struct WarpBoard {
                 draws += 18;
                 if ((K | S | C) == 0) {
                     // no cell can be accepted: the loop runs its 9 iterations, 2 draws each
-#pragma unroll 2
-                    for (int i = 0; i < 18; i++) mt.next_state(prm.mat1, prm.mat2);
+                    jump18(jt);
                 } else {
 #pragma unroll 1
                     for (int k = 0; k < 9; k++) {
@@ -219,7 +244,7 @@ struct WarpBoard {
                         const unsigned m = K | (k < 6 ? S : 0u) | (k < 4 ? C : 0u);
                         if (c9 != 4 && ((m >> (4 * c8)) & 1u)) {    // centre (c9 == 4) is occupied
                             draws -= 2 * (8 - k);
-                            return (er - 1 + a) * N + (ec - 1 + b);
+                            return lm + (a - 1) * W + (b - 1);
                         }
                     }
                 }
@@ -229,14 +254,14 @@ struct WarpBoard {
                 draws += 2;
                 const int row = (int)(rand15(prm) % (uint32_t)N);
                 const int cl = (int)(rand15(prm) % (uint32_t)N);
-                const int idx = row * N + cl;
+                const int idx = row * W + cl + (W + 1);
                 bool bad = fCol(w0[idx]) != 0;
                 if (count == kEndingThreshold) {                    // even if the 100th draw passed
                     ending = 1;
                     break;
                 }
                 if (!bad) {
-                    bad = (eval_cells(agent, row, cl) & F_BAD) != 0;
+                    bad = (eval_cells(agent, idx) & F_BAD) != 0;
                     if (!bad) return idx;
                 }
             }
@@ -260,14 +285,10 @@ struct WarpBoard {
                 w0[k] = pack0(k, k, 0);
             }
             head = k;
-            const int i = k / N, j = k - i * N;
-#pragma unroll 1
+#pragma unroll
             for (int d = 0; d < 4; d++) {                           // one liberty back, :323-326
-                const int nb = k + (d == 0 ? -N : (d == 1 ? -1 : (d == 2 ? N : 1)));
-                const bool on = d == 0 ? i > 0 : (d == 1 ? j > 0 : (d == 2 ? i + 1 < N : j + 1 < N));
-                if (!on) continue;
-                const uint32_t v = w0[nb];
-                if (fCol(v) != 0 && fCol(v) != agent) w1[fA(v)] += 1u;
+                const uint32_t v = w0[k + (d == 0 ? -W : (d == 1 ? -1 : (d == 2 ? W : 1)))];
+                if (fCol(v) == 3 - agent) w1[fA(v)] += 1u;
             }
             if (single) ko_key = (agent << 16) | k;                 // :328-333
             k = nx;
@@ -276,7 +297,6 @@ struct WarpBoard {
 
     // Board::put, Board.cpp:68-177 (warp-uniform; the point is empty)
     __device__ __forceinline__ void put(int agent, int idx) {
-        const int i = idx / N, j = idx - i * N;
         stones++;
         ko_key = -1;
         {                                                           // unlink from the empty list, :105-118
@@ -294,12 +314,10 @@ struct WarpBoard {
         w1[idx] = (uint32_t)idx << 16;
         // lane d (mod 4) looks at neighbour d (up, left, down, right) once: own liberties before
         // any capture (:123-127) and the set of directions that hold a stone
-        const int dl = lane & 3;
-        const int nb_l = idx + (dl == 0 ? -N : (dl == 1 ? -1 : (dl == 2 ? N : 1)));
-        const bool on_l = dl == 0 ? i > 0 : (dl == 1 ? j > 0 : (dl == 2 ? i + 1 < N : j + 1 < N));
-        const int col_l = on_l ? fCol(w0[nb_l]) : -1;
+        const int nb_l = idx + off_nb;
+        const int col_l = fCol(w0[nb_l]);
         const int hp_self = __popc(__ballot_sync(kFull, col_l == 0) & 15u);
-        unsigned todo = (__ballot_sync(kFull, col_l > 0) & 15u) | 16u;
+        unsigned todo = (__ballot_sync(kFull, is_stone(col_l)) & 15u) | 16u;
         // up, left, down, right (:129-164), then the stone's own string (:165-167) as step 4
 #pragma unroll 1
         while (todo) {
@@ -342,14 +360,19 @@ struct WarpBoard {
         if (agent == 1) last0 = idx; else last1 = idx;             // :171
     }
 
-    // Board::countScore(agent) - countScore(enemy), Board.cpp:910-925, strided over the lanes
+    // Board::countScore(agent) - countScore(enemy), Board.cpp:910-925, strided over the lanes:
+    // an empty point counts for the colour of its LEFT neighbour (right one in column 0)
     __device__ __forceinline__ int score_diff(int agent) const {
         int d = 0;
 #pragma unroll 1
-        for (int idx = lane; idx < NN; idx += 32) {
-            const int i = idx / N, j = idx - i * N;
+        for (int idx = W + lane; idx < NP - W; idx += 32) {
             const int c = fCol(w0[idx]);
-            const int owner = c != 0 ? c : fCol(w0[j > 0 ? idx - 1 : idx + 1]);
+            if (c == kBorder) continue;
+            int owner = c;
+            if (c == 0) {
+                const int l = fCol(w0[idx - 1]);
+                owner = l != kBorder ? l : fCol(w0[idx + 1]);
+            }
             d += (owner == agent) - (owner == 3 - agent);
         }
 #pragma unroll
@@ -358,21 +381,24 @@ struct WarpBoard {
     }
 };
 
-// per-warp shared memory: w0[NN], w1[NN], scratch[NN] (16 bit), rounded to 32 words
+// per-warp shared memory: w0[NP], w1[NP], scratch[NN] (16 bit), rounded to 32 words
 template <int N>
-struct BoardWords { static constexpr int value = ((2 * N * N + (N * N + 1) / 2 + 31) / 32) * 32; };
+struct BoardWords {
+    static constexpr int NP = (N + 2) * (N + 2);
+    static constexpr int value = ((2 * NP + (N * N + 1) / 2 + 31) / 32) * 32;
+};
 
 template <int N, int WARPS, int BLOCKS_PER_SM>
 __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel(const KernelArgs a) {
     extern __shared__ uint32_t smem[];
-    constexpr int NN = N * N;
+    typedef WarpBoard<N> WB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    WarpBoard<N> bd;
+    WB bd;
     bd.w0 = smem + (size_t)warp * BoardWords<N>::value;
-    bd.w1 = bd.w0 + NN;
-    bd.scratch = reinterpret_cast<uint16_t*>(bd.w1 + NN);
-    bd.lane = lane;
+    bd.w1 = bd.w0 + WB::NP;
+    bd.scratch = reinterpret_cast<uint16_t*>(bd.w1 + WB::NP);
+    bd.init_lane(lane);
 
     unsigned long long moves = 0, draws = 0;
     unsigned int faults = 0, played = 0;
@@ -386,25 +412,25 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         const int64_t g = (int64_t)l * a.shard_count + a.shard_rank;
         const int s = (int)(g / a.P);
         const int64_t p = g - (int64_t)s * a.P;
-        const Position& pos = a.starts[s];
+        const PaddedPosition& pos = a.pstarts[s];
         const StartDesc d = a.descs[s];
 
         __syncwarp();
 #pragma unroll 1
-        for (int i = lane; i < NN; i += 32) {                       // Board::clone, Board.cpp:216-254
+        for (int i = lane; i < WB::NP; i += 32) {                   // Board::clone, Board.cpp:216-254
             bd.w0[i] = pos.w0[i];
             bd.w1[i] = pos.w1[i];
         }
         bd.head = pos.head;
-        bd.stones = pos.num_black + pos.num_white;
-        bd.ko_key = pos.ko ? ((pos.ko_col << 16) | pos.ko_idx) : -1;
+        bd.stones = pos.stones;
+        bd.ko_key = pos.ko_key_col > 0 ? ((pos.ko_key_col << 16) | pos.ko_idx) : -1;
         bd.last0 = pos.last[0];
         bd.last1 = pos.last[1];
         bd.ending = pos.ending;
         bd.draws = 0;
         __syncwarp();
         {
-            // tinymt32_init (RFC 8682), rolled
+            // tinymt32_init (RFC 8682)
             uint32_t st[4] = {playout_seed(a.seed_base, d.position_id, d.cand_idx, (uint64_t)p),
                               a.rng.mat1, a.rng.mat2, a.rng.tmat};
 #pragma unroll
@@ -426,7 +452,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
 #pragma unroll 1
         for (int t = 0;; t++) {
             const int colour = (t & 1) ? 3 - first : first;
-            const int r = bd.random_piece(a.rng, colour);
+            const int r = bd.random_piece(a.rng, a.jump18, colour);
             if (r >= 0) {
                 bd.put(colour, r);
                 mv++;
@@ -481,6 +507,51 @@ cudaError_t launch_w(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchIn
 }
 
 }  // namespace
+
+// Host side of the padded layout: re-index a Position (board_ops.h) into a PaddedPosition.
+void to_padded(const Position& p, PaddedPosition* out) {
+    const int n = p.n, w = n + 2;
+    auto pad = [&](int idx) { return (idx / n + 1) * w + (idx % n + 1); };
+    for (int i = 0; i < kMaxNP; i++) { out->w0[i] = (uint32_t)kBorder << 20; out->w1[i] = 0; }
+    for (int idx = 0; idx < n * n; idx++) {
+        const uint32_t v0 = p.w0[idx], v1 = p.w1[idx];
+        const int col = (int)((v0 >> 20) & 3u);
+        const int a = (int)(v0 & 1023u), b = (int)((v0 >> 10) & 1023u);
+        const int pa = pad(a), pb = (col != 0 && b == kNil) ? kNil : pad(b);
+        out->w0[pad(idx)] = (uint32_t)pa | ((uint32_t)pb << 10) | ((uint32_t)col << 20);
+        const bool is_root = col != 0 && a == idx;                  // hp/tail are meaningful at roots only
+        out->w1[pad(idx)] = is_root ? ((v1 & 0xffffu) | ((uint32_t)pad((int)(v1 >> 16)) << 16)) : 0u;
+    }
+    out->head = (int16_t)(p.head >= 0 ? pad(p.head) : -1);
+    out->stones = (int16_t)(p.num_black + p.num_white);
+    out->ko_key_col = (int16_t)(p.ko ? p.ko_col : 0);
+    out->ko_idx = (int16_t)(p.ko ? pad(p.ko_idx) : 0);
+    out->last[0] = (int16_t)(p.last[0] >= 0 ? pad(p.last[0]) : -1);
+    out->last[1] = (int16_t)(p.last[1] >= 0 ? pad(p.last[1]) : -1);
+    out->ending = p.ending;
+    out->pad = 0;
+}
+
+// T^18 of TinyMT32 as a nibble table (see JumpTable): column b of T^18 is the state reached from
+// the unit vector e_b after 18 transitions (the transition is linear over GF(2)).
+void build_jump18(const RngParams& prm, JumpTable* out) {
+    uint32_t col[128][4];
+    for (int b = 0; b < 128; b++) {
+        TinyMT t;
+        t.s0 = t.s1 = t.s2 = t.s3 = 0;
+        (b < 32 ? t.s0 : (b < 64 ? t.s1 : (b < 96 ? t.s2 : t.s3))) = 1u << (b & 31);
+        for (int i = 0; i < 18; i++) t.next_state(prm.mat1, prm.mat2);
+        col[b][0] = t.s0; col[b][1] = t.s1; col[b][2] = t.s2; col[b][3] = t.s3;
+    }
+    for (int l = 0; l < 32; l++)
+        for (int v = 0; v < 16; v++) {
+            uint32_t acc[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; k++)
+                if (v & (1 << k))
+                    for (int wd = 0; wd < 4; wd++) acc[wd] ^= col[4 * l + k][wd];
+            out->e[l * 16 + v] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+        }
+}
 
 cudaError_t launch_playout_warp(int n, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
     // 8 warps per block, 4 blocks per SM: 32 resident playouts per SM, 64 registers per thread
