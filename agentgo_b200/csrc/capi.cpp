@@ -180,7 +180,7 @@ int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
 int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_root, uint64_t seed_base,
                 int* row, int* col, int* is_pass, agb_stats* stats) {
     if (!h || !row || !col || !is_pass) return AGB_ERR_INVALID;
-    if (P_per_candidate <= 0 || P_root <= 0) return h->e->fail(AGB_ERR_INVALID, "bad playout counts");
+    if (P_per_candidate == 0 || P_root <= 0) return h->e->fail(AGB_ERR_INVALID, "bad playout counts");
     AGB_GUARD_BEGIN
     return h->e->genmove(colour, P_per_candidate, P_root, seed_base, row, col, is_pass, stats);
     AGB_GUARD_END(h)

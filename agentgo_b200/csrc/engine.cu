@@ -325,6 +325,7 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
     *is_pass = 1; *row = -1; *col = -1;
     if (C > 0) {
         std::vector<int64_t> cw(C), csp(C), csn(C);
+        if (P_cand < 0) P_cand = (-P_cand + C - 1) / C;      // fixed budget per genmove, split over candidates
         st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false);
         if (st) return st;
         if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1))) return st;

@@ -199,7 +199,9 @@ int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
  * AMAF terms, which are outside the flat-MC path): root playouts -> avrg_win,
  * candidate filter, P playouts per candidate, argmax of
  * sum_pos + cnsv*sum_neg.  *is_pass = 1 when no candidate exists.  The move
- * is NOT played on the engine's board (the caller does, GTPAdapter.cpp:78). */
+ * is NOT played on the engine's board (the caller does, GTPAdapter.cpp:78).
+ * P_per_candidate < 0: |P_per_candidate| is a fixed playout budget per genmove,
+ * split evenly (rounded up) over the candidates.                              */
 int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_root,
                 uint64_t seed_base, int* row, int* col, int* is_pass, agb_stats* stats);
 

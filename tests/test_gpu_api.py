@@ -1,0 +1,182 @@
+"""GPU tests of the rest of the C ABI: batch, genmove, sharding, edge cases, full-size parity."""
+import numpy as np
+import pytest
+
+import agentgo_b200 as ag
+from oracle import pyoracle as po
+from util import golden, split_moves
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [ag.KERNEL_THREAD, ag.KERNEL_WARP]
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_golden_root_prefix(built_lib, kernel):
+    for n in (9, 13, 19):
+        g = golden("root_%d.npz" % n)
+        P = int(g["P"])
+        w, sp, sn, d, st = ag.Engine(n, kernel=kernel).playouts(1, None, P, seed_base=int(g["seed_base"]), want_diffs=True)
+        assert (d[0] == g["diffs"]).all()
+        assert (w[0], sp[0], sn[0]) == (g["wins"][0], g["sum_pos"][0], g["sum_neg"][0])
+        assert st["moves"] == int(g["moves"]) and st["rng_draws"] == int(g["rng_draws"])
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_golden_candidates(built_lib, kernel):
+    for name in ("cands_9.npz", "cands_13_midgame.npz"):
+        g = golden(name)
+        e = ag.Engine(int(g["n"]), kernel=kernel)
+        if "moves" in g.files:
+            e.replay(g["moves"])
+        pid = int(g["position_id"]) if "position_id" in g.files else 0
+        w, sp, sn, d, _ = e.playouts(int(g["colour"]), [tuple(int(x) for x in rc) for rc in g["cands"]], int(g["P"]),
+                                     avrg_win=int(g["avrg_win"]), seed_base=int(g["seed_base"]), position_id=pid,
+                                     want_diffs=True)
+        assert (d == g["diffs"]).all()
+        assert (w == g["wins"]).all() and (sp == g["sum_pos"]).all() and (sn == g["sum_neg"]).all()
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_golden_midgame_batch(built_lib, kernel):
+    """config 3 subset: 16 mid-game 19x19 positions through agb_playouts_batch."""
+    g = golden("midgame_19.npz")
+    moves = split_moves(g)
+    ids = [int(x) for x in g["position_ids"]]
+    P = int(g["P"])
+    e = ag.Engine(19, kernel=kernel)
+    for bi in range(len(moves)):     # position ids are not contiguous: one call per position id
+        w, sp, sn, d, _ = e.playouts_batch([(moves[bi], int(g["to_move"][bi]))], P, seed_base=int(g["seed_base"]),
+                                           first_position_id=ids[bi], want_diffs=True)
+        assert (d[0] == g["diffs"][bi]).all(), bi
+        assert (w[0], sp[0], sn[0]) == tuple(g["sums"][bi])
+
+
+def test_batch_many_positions_vs_oracle(built_lib):
+    n, B, P = 19, 24, 400
+    pos = []
+    for k in range(B):
+        mv = po.OracleBoard(n, "best").random_game(1, 30 + 9 * k, 7000 + k)
+        pos.append((mv, 1 + len(mv) % 2))
+    w, sp, sn, d, st = ag.Engine(n).playouts_batch(pos, P, seed_base=5, first_position_id=100, want_diffs=True)
+    assert st["playouts"] == B * P
+    for k in (0, 7, 23):
+        ow, osp, osn, od = po.OracleBoard(n, "best").replay(pos[k][0]).playouts(pos[k][1], None, P, seed_base=5,
+                                                                                position_id=100 + k, threads=0)
+        assert (d[k] == od[0]).all() and (w[k], sp[k], sn[k]) == (ow[0], osp[0], osn[0])
+
+
+def test_sharded_engines_partition_the_ids(built_lib):
+    n, P = 13, 600
+    cands = [(3, 3), (6, 6), (9, 2)]
+    full = ag.Engine(n).playouts(ag.BLACK, cands, P, avrg_win=-1, want_diffs=True)
+    acc = [np.zeros(3, dtype=np.int64) for _ in range(3)]
+    merged = np.full((3, P), -32768, dtype=np.int16)
+    for r in range(3):
+        e = ag.Engine(n, shard_rank=r, shard_count=3)
+        w, sp, sn, d, st = e.playouts(ag.BLACK, cands, P, avrg_win=-1, want_diffs=True)
+        assert st["playouts"] == len(range(r, 3 * P, 3))
+        for a, x in zip(acc, (w, sp, sn)):
+            a += x
+        mine = d.reshape(-1)[r::3]
+        assert (mine != -32768).all()
+        other = np.delete(d.reshape(-1), np.arange(r, 3 * P, 3))
+        assert (other == -32768).all()          # entries of other shards are left untouched
+        merged.reshape(-1)[r::3] = mine
+    assert (merged == full[3]).all()
+    for a, x in zip(acc, full[:3]):
+        assert (a == x).all()
+
+
+def test_allreduce_hook_is_called_on_the_counters(built_lib):
+    import ctypes
+    calls = []
+    e = ag.Engine(9, shard_rank=0, shard_count=2)
+    e.set_allreduce(lambda ptr, count, stream: calls.append((ptr, count, stream)) or 0)
+    e.playouts(ag.BLACK, [(4, 4), (2, 2)], 50)
+    assert len(calls) == 1 and calls[0][1] == 6 and calls[0][0] == e.counters_dev() and calls[0][2] == e.stream()
+
+
+def test_edge_cases(built_lib):
+    e = ag.Engine(9)
+    # P = 1
+    w, sp, sn, d, st = e.playouts(ag.WHITE, None, 1, want_diffs=True)
+    od = po.OracleBoard(9, "best").playouts(2, None, 1, threads=1)[3]
+    assert d[0, 0] == od[0, 0] and st["playouts"] == 1
+    # occupied candidate is refused
+    e.play(ag.BLACK, 4, 4)
+    with pytest.raises(ag.AgbError) as ex:
+        e.playouts(ag.WHITE, [(4, 4)], 10)
+    assert ex.value.status == -2
+    with pytest.raises(ag.AgbError):
+        e.playouts(ag.WHITE, [(9, 0)], 10)
+    with pytest.raises(ag.AgbError):
+        e.playouts(3, None, 10)
+    # nearly full board with a ko on the root: game ends quickly, passes happen
+    n = 9
+    mv = po.OracleBoard(n, "best").random_game(1, 3 * n * n, 31337)
+    ob = po.OracleBoard(n, "best").replay(mv)
+    e2 = ag.Engine(n).replay(mv)
+    for kern in KERNELS:
+        e3 = ag.Engine(n, kernel=kern).replay(mv)
+        w, sp, sn, d, _ = e3.playouts(1, None, 300, want_diffs=True)
+        assert (d == ob.playouts(1, None, 300, threads=0)[3]).all()
+    assert (e2.export_state() == ob.export_state()).all()
+
+
+def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base):
+    w, sp, sn, _ = ob.playouts(colour, None, P_root, seed_base=seed_base, want_diffs=False, threads=0)
+    tot = int(sp[0] + sn[0])
+    avrg = abs(tot) // P_root * (1 if tot >= 0 else -1)          # C truncation, AgentGo.cpp:447
+    st = ob.export_state()
+    cands = []
+    for i in range(n):
+        for j in range(n):
+            if (ob.check("true_eye", colour, i, j) or st[16 + i * n + j] != 0 or ob.check("suicide", colour, i, j)
+                    or ob.check("no_sense", colour, i, j) or ob.check("compete", colour, i, j)):
+                continue
+            cands.append((i, j))
+    marks = {}
+    if cands:
+        w, sp, sn, _ = ob.playouts(colour, cands, P_cand, avrg_win=avrg, seed_base=seed_base + 1, want_diffs=False, threads=0)
+        cnsv = 2.0 ** (avrg * 0.01)
+        for c, a, b in zip(cands, sp, sn):
+            marks[c] = 2.0 * 100.0 * (float(a) + cnsv * float(b))
+    best, arg = None, None
+    for i in range(n):
+        for j in range(n):
+            if st[16 + i * n + j] == 0 and not ob.check("true_eye", colour, i, j) and \
+                    not ob.check("suicide", colour, i, j) and not ob.check("compete", colour, i, j):
+                m = marks.get((i, j), 0.0)
+                if best is None or m > best:
+                    best, arg = m, (i, j)
+    return arg if cands else None
+
+
+def test_genmove_matches_oracle_restatement(built_lib):
+    for n, seed in ((9, 11), (13, 12)):
+        mv = po.OracleBoard(n, "best").random_game(1, n * n // 2, seed)
+        colour = 1 + len(mv) % 2
+        ob = po.OracleBoard(n, "best").replay(mv)
+        e = ag.Engine(n).replay(mv)
+        got, st = e.genmove(colour, 60, 200, seed_base=777)
+        assert got == _oracle_genmove(ob, n, colour, 60, 200, 777)
+        assert st["playouts"] > 200
+
+
+def test_full_size_config2_bit_exact(built_lib):
+    """BASELINE.json configs[1]: 19x19 empty board, 1 000 000 root-mode playouts, every per-playout
+    diff and the three counters against the oracle (the compiled reference when present)."""
+    P = 1000000
+    w, sp, sn, d, st = ag.Engine(19).playouts(ag.BLACK, None, P, want_diffs=True)
+    assert st["playouts"] == P and st["faults"] == 0
+    # size-independent properties
+    dd = d[0].astype(np.int64)
+    assert w[0] == (dd >= 0).sum() and sp[0] == dd[dd >= 0].sum() and sn[0] == dd[dd < 0].sum()
+    assert np.abs(dd).max() <= 361
+    g = golden("root_19.npz")
+    assert (d[0][:int(g["P"])] == g["diffs"]).all()
+    ow, osp, osn, od, ost = po.OracleBoard(19, "best").playouts(1, None, P, threads=0, with_stats=True)
+    assert (d == od).all()
+    assert (w[0], sp[0], sn[0]) == (ow[0], osp[0], osn[0])
+    assert st["moves"] == ost["moves"] and st["rng_draws"] == ost["rng_draws"]

@@ -1,0 +1,58 @@
+"""GTP command surface: wire format of AgentGo/GTPAdapter.cpp (position-only engine on CPU)."""
+import os
+import subprocess
+
+import pytest
+
+import agentgo_b200 as ag
+
+GTP = os.path.join(ag.HERE, "agentgo_gtp")
+
+
+def gtp(cmds, *args):
+    r = subprocess.run([GTP] + list(args), input="\n".join(cmds) + "\n", capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    return r.stdout
+
+
+def test_wire_format_without_gpu(built_lib):
+    out = gtp(["name", "VERSION", "protocol_version", "list_commands", "", "komi 6.5", "boardsize 19",
+               "clear_board", "play b D4", "play W q16", "play b pass", "play b D4", "play x D4",
+               "frobnicate 1 2", "genmove x", "quit", "name"], "--device", "-1")
+    exp = ("= AgentGo\n\n" "= 0.0.1\n\n" "= 2\n\n"
+           "= protocol_version\nname\nversion\nlist_commands\nquit\nboardsize\nclear_board\nkomi\nplay\ngenmove\n\n"
+           "= \n\n"            # komi
+           "=\n\n"             # boardsize (no space, GTPAdapter.cpp:147)
+           "=\n\n"             # clear_board
+           "= \n\n"            # play b D4
+           "= \n\n"            # play W q16 (colour and letter are case-insensitive)
+           "= \n\n"            # play b pass: acknowledged, board untouched (GTPAdapter.cpp:107-113)
+           "? unknown command : play b D4\n\n"      # occupied: the reference would AG_PANIC
+           "? unknown command : play x D4\n\n"
+           "? unknown command : frobnicate 1 2\n\n"
+           "? unknown command : genmove x\n\n"
+           "=\n\n")            # quit; nothing after it
+    assert out == exp
+
+
+def test_coordinates_skip_letter_i(built_lib):
+    # GaCharToInt / GaIntToChar (GTPAdapter.cpp:19-20): a..h -> 0..7, j -> 8; the LETTER is the row
+    e = ag.Engine(19, device=-1)
+    out = gtp(["boardsize 19", "play b J1", "play w H19", "play b T3", "quit"], "--device", "-1")
+    assert out.count("= \n\n") == 3
+
+
+@pytest.mark.gpu
+def test_genmove_and_selfplay_on_gpu(built_lib):
+    out = gtp(["boardsize 9", "clear_board", "play b E5", "genmove w", "genmove b", "quit"],
+              "--playouts", "64", "--root-playouts", "128")
+    lines = [l for l in out.split("\n\n") if l]
+    assert lines[0] == "=" and lines[1] == "=" and lines[2] == "= "
+    for l in lines[3:5]:
+        assert l.startswith("= ") and (l[2:] == "pass" or (l[2] in "ABCDEFGHJ" and 1 <= int(l[3:]) <= 9))
+    r = subprocess.run([GTP, "--boardsize", "9", "--selfplay", "--playouts", "32", "--root-playouts", "64",
+                        "--max-moves", "400"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    import json
+    sp = json.loads(r.stdout.strip().splitlines()[-1])["selfplay"]
+    assert sp["genmoves"] >= 20 and sp["device_ms_median"] > 0
