@@ -52,7 +52,7 @@ def workload(per_gpu, n_gpus):
             "board_size": BOARD, "playouts_per_step": per_gpu * n_gpus, "playouts_per_gpu": per_gpu,
             "parallelism": "playout ids sharded g %% %d == rank, one NCCL allreduce of 3 int64 per step" % n_gpus
             if n_gpus > 1 else "single GPU",
-            "l2": "L2 flushed between timed steps (256 MiB write); inputs are 2.9 KB"}
+            "l2": "L2 flushed between timed steps (256 MiB write); inputs are 3.5 KB"}
 
 
 class ClockSampler:
@@ -258,7 +258,7 @@ def run_b200(args):
         rates, info = cpu_reference(sample_seconds=args.cpu_seconds)
         cpu = {"value": rates[0][0], "unit": UNIT, "cores": info["cores"], "threads": info["threads"],
                "kind": info["kind"], "sample": info["sample"], "seconds": rates[0][1]}
-    pos_bytes = 2 * 361 * 4 + 24 + 16          # Position + StartDesc
+    pos_bytes = 2 * 441 * 4 + 16 + 16          # PaddedPosition + StartDesc
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": workload(args.playouts, world),
