@@ -88,6 +88,14 @@ struct WarpBoard {
         mt.next_state(p.mat1, p.mat2);
         return mt.temper(p.tmat) >> 17;
     }
+    // rand() % M for a 15-bit value and a small constant M: one IMAD.HI and one IMAD
+    // (q = floor(v * ceil(2^32 / M) / 2^32) is exact for v < 2^15)
+    template <uint32_t M>
+    __device__ __forceinline__ uint32_t rand_mod(const RngParams& p) {
+        const uint32_t v = rand15(p);
+        const uint32_t q = __umulhi(v, (uint32_t)((0x100000000ull + M - 1) / M));
+        return v - q * M;
+    }
 
     // advance the generator by 18 steps (values not needed): s' = T^18 s over GF(2)
     __device__ __forceinline__ void jump18(const JumpTable* __restrict__ jt) {
@@ -237,14 +245,14 @@ struct WarpBoard {
                 } else {
 #pragma unroll 1
                     for (int k = 0; k < 9; k++) {
-                        const int a = (int)(rand15(prm) % 3u);
-                        const int b = (int)(rand15(prm) % 3u);
-                        const int c9 = a * 3 + b;
-                        const int c8 = c9 - (c9 > 4);
+                        const uint32_t a = rand_mod<3>(prm);
+                        const uint32_t b = rand_mod<3>(prm);
+                        const uint32_t c9 = a * 3u + b;
+                        const uint32_t c8 = c9 - (c9 > 4u);
                         const unsigned m = K | (k < 6 ? S : 0u) | (k < 4 ? C : 0u);
                         if (c9 != 4 && ((m >> (4 * c8)) & 1u)) {    // centre (c9 == 4) is occupied
                             draws -= 2 * (8 - k);
-                            return lm + (a - 1) * W + (b - 1);
+                            return lm + (int)(a * W + b) - (W + 1);
                         }
                     }
                 }
@@ -252,9 +260,9 @@ struct WarpBoard {
 #pragma unroll 1
             for (int count = 1;; count++) {                         // :382-406
                 draws += 2;
-                const int row = (int)(rand15(prm) % (uint32_t)N);
-                const int cl = (int)(rand15(prm) % (uint32_t)N);
-                const int idx = row * W + cl + (W + 1);
+                const uint32_t row = rand_mod<N>(prm);
+                const uint32_t cl = rand_mod<N>(prm);
+                const int idx = (int)(row * W + cl + (W + 1));
                 bool bad = fCol(w0[idx]) != 0;
                 if (count == kEndingThreshold) {                    // even if the 100th draw passed
                     ending = 1;
