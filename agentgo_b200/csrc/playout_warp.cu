@@ -49,11 +49,6 @@ __device__ __forceinline__ uint32_t pack0(int a, int b, int col) {
     return (uint32_t)a | ((uint32_t)b << 10) | ((uint32_t)col << 20);
 }
 
-// flag bits returned by eval_cells
-enum : uint32_t {
-    F_EMPTY = 1u, F_KILL = 2u, F_SURVIVE = 4u, F_CHASE = 8u, F_BAD = 16u, F_RESERVE = 32u
-};
-
 template <int N>
 struct WarpBoard {
     static constexpr int W = N + 2;
@@ -109,68 +104,66 @@ struct WarpBoard {
     }
 
     // Lane-parallel evaluation of up to 8 points at once: lane = 4*cell + dir evaluates
-    // neighbour `dir` (up, left, down, right) of its cell `cidx` (padded index; a border cell
-    // yields no F_EMPTY); the four lanes of a cell return the same flags.  Restates
-    // checkSuicide/Kill/Survive/Dying/Chase/TrueEye/Compete (Board.cpp:480-755);
-    // F_BAD = dying | true eye | suicide | ko (the filter of both sampling phases),
-    // F_RESERVE = true eye | suicide | ko (complex mode, no checkDying).
-    __device__ __forceinline__ uint32_t eval_cells(int agent, int cidx) const {
-        const int dir = lane & 3;
-        const int sh = lane & ~3;
-        const int ccol = fCol(w0[cidx]);
-        const bool cell_on = ccol != kBorder;
+    // neighbour `dir` (up, left, down, right) of its cell `cidx` (padded index; a border cell is
+    // never `empty`); the four lanes of a cell hold the same result.  Restates
+    // checkSuicide/Kill/Survive/Dying/Chase/TrueEye/Compete (Board.cpp:480-755).
+    //   bad     = dying | true eye | suicide | ko   (the filter of both sampling phases)
+    //   reserve = true eye | suicide | ko           (complex mode: no checkDying, :425-427)
+    // Force-inlined at three call sites; each site only reads the fields it needs, so the
+    // compiler drops the rest (complex mode needs neither the friend sums nor survive/chase).
+    struct Eval {
+        bool empty, kill, survive, chase, bad, reserve;
+    };
+    __device__ __forceinline__ Eval eval_cells(int agent, int cidx) const {
+        const unsigned nib = 15u << (lane & ~3);                    // this cell's four lanes
+        const uint32_t wc = w0[cidx];
+        const bool cell_on = fCol(wc) != kBorder;
         const uint32_t wn = w0[cell_on ? cidx + off_nb : 0];        // w0[0] is a border cell
         const int ncol = fCol(wn);
         const bool nb_stone = is_stone(ncol);
-        const int root = nb_stone ? fA(wn) : -1 - dir;              // distinct negatives never match
+        const int root = nb_stone ? fA(wn) : -1 - (lane & 3);       // distinct negatives per direction
         const int hp = (int)(w1[nb_stone ? root : 0] & 0xffffu);
 
-        const int r1 = __shfl_xor_sync(kFull, root, 1);
-        const int r2 = __shfl_xor_sync(kFull, root, 2);
-        const int r3 = __shfl_xor_sync(kFull, root, 3);
-        const int mult = 1 + (r1 == root) + (r2 == root) + (r3 == root);
-        const bool first = !((r1 == root && (dir ^ 1) < dir) || (r2 == root && (dir ^ 2) < dir) ||
-                             (r3 == root && (dir ^ 3) < dir));
-        const int left = hp - mult;
+        // strings seen from several directions count once, with their multiplicity as minus_hp
+        // (Board.cpp:506-515): lanes of this cell holding the same root
+        const unsigned same = __match_any_sync(kFull, root) & nib;
+        const int left = hp - __popc(same);
+        const bool first = (same & ((1u << lane) - 1u)) == 0;
         const bool enemy = ncol == 3 - agent;
         const bool frnd = ncol == agent;
 
-        const unsigned b_empty = __ballot_sync(kFull, ncol == 0);
-        const unsigned b_ecap = __ballot_sync(kFull, enemy && left == 0);
-        const unsigned b_eatari = __ballot_sync(kFull, enemy && left == 1);
-        const unsigned b_fcap = __ballot_sync(kFull, frnd && left == 0);
-        const unsigned b_fsafe = __ballot_sync(kFull, frnd && left > 0);
+        const int n_empty = __popc(__ballot_sync(kFull, ncol == 0) & nib);
+        const bool ecap = (__ballot_sync(kFull, enemy && left == 0) & nib) != 0;
+        const bool eatari = (__ballot_sync(kFull, enemy && left == 1) & nib) != 0;
+        const bool fcap = (__ballot_sync(kFull, frnd && left == 0) & nib) != 0;
+        const bool fsafe = (__ballot_sync(kFull, frnd && left > 0) & nib) != 0;
         int fsum = (frnd && first) ? left : 0;
         fsum += __shfl_xor_sync(kFull, fsum, 1);
         fsum += __shfl_xor_sync(kFull, fsum, 2);
         int fmin = frnd ? hp : 9999;
         fmin = min(fmin, __shfl_xor_sync(kFull, fmin, 1));
         fmin = min(fmin, __shfl_xor_sync(kFull, fmin, 2));
-
-        const int n_empty = __popc((b_empty >> sh) & 15u);
-        const bool ecap = ((b_ecap >> sh) & 15u) != 0;
-        const bool eatari = ((b_eatari >> sh) & 15u) != 0;
-        const bool fcap = ((b_fcap >> sh) & 15u) != 0;
-        const bool fsafe = ((b_fsafe >> sh) & 15u) != 0;
         const int tot = n_empty + fsum;
         const bool suicide = n_empty == 0 && !ecap && !fsafe;       // Board.cpp:480-524
-        const bool survive = fcap && (ecap || tot > fmin);          // :565-626
         const bool dying = !ecap && tot == 1;                       // :628-679
-        const bool chase = eatari && tot > 1;                       // :681-733
 
         // Board::checkTrueEye, :735-751 — lane `dir` also looks at one diagonal; a cell is on the
         // edge iff one of its orthogonal neighbours is a border cell
-        const unsigned b_off = __ballot_sync(kFull, ncol == kBorder);
-        const unsigned b_own = __ballot_sync(kFull, ncol == kBorder || ncol == agent);
+        const bool edge = (__ballot_sync(kFull, ncol == kBorder) & nib) != 0;
+        const bool own4 = (__ballot_sync(kFull, ncol != kBorder && ncol != agent) & nib) == 0;
         const int dcol = fCol(w0[cell_on ? cidx + off_dg : 0]);
-        const unsigned b_diag = __ballot_sync(kFull, dcol == 3 - agent);
-        const int cnt = __popc((b_diag >> sh) & 15u);
-        const bool edge = ((b_off >> sh) & 15u) != 0;
-        const bool eye = ((b_own >> sh) & 15u) == 15u && cnt < (edge ? 1 : 2);
+        const int cnt = __popc(__ballot_sync(kFull, dcol == 3 - agent) & nib);
+        const bool eye = own4 && cnt < (edge ? 1 : 2);
         const bool ko = ko_key == ((agent << 16) | cidx);           // :753-755
-        const bool reserve = eye || suicide || ko;
-        return (ccol == 0 ? F_EMPTY : 0u) | (ecap ? F_KILL : 0u) | (survive ? F_SURVIVE : 0u) |
-               (chase ? F_CHASE : 0u) | ((reserve || dying) ? F_BAD : 0u) | (reserve ? F_RESERVE : 0u);
+
+        Eval e;
+        e.empty = fCol(wc) == 0;
+        e.kill = ecap;                                              // :526-563
+        e.survive = fcap && (ecap || tot > fmin);                   // :565-626
+        e.chase = eatari && tot > 1;                                // :681-733
+        e.reserve = eye || suicide || ko;
+        e.bad = e.reserve || dying;
+        return e;
     }
 
     // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags): the empty points
@@ -194,8 +187,8 @@ struct WarpBoard {
         for (int base = 0; base < n_e; base += 8) {
             const int k = base + (lane >> 2);
             const int idx = k < n_e ? (int)scratch[k] : 0;          // 0 is a border cell
-            const uint32_t f = eval_cells(agent, idx);
-            const bool res = (f & F_EMPTY) && (f & F_RESERVE);
+            const Eval f = eval_cells(agent, idx);
+            const bool res = f.empty && f.reserve;
             if (res && (lane & 3) == 0) w0[idx] |= (1u << 22);      // addReserve, :757-761
             reserved_total += __popc(__ballot_sync(kFull, res) & 0x11111111u);
         }
@@ -233,11 +226,11 @@ struct WarpBoard {
         if (!complex_mode) {
             const int lm = agent == 1 ? last1 : last0;              // opponent's last move
             if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
-                const uint32_t f = eval_cells(agent, lm + off_cell);
-                const bool ok = (f & F_EMPTY) && !(f & F_BAD);
-                const unsigned K = __ballot_sync(kFull, ok && (f & F_KILL));
-                const unsigned S = __ballot_sync(kFull, ok && (f & F_SURVIVE));
-                const unsigned C = __ballot_sync(kFull, ok && (f & F_CHASE));
+                const Eval f = eval_cells(agent, lm + off_cell);
+                const bool ok = f.empty && !f.bad;
+                const unsigned K = __ballot_sync(kFull, ok && f.kill);
+                const unsigned S = __ballot_sync(kFull, ok && f.survive);
+                const unsigned C = __ballot_sync(kFull, ok && f.chase);
                 draws += 18;
                 if ((K | S | C) == 0) {
                     // no cell can be accepted: the loop runs its 9 iterations, 2 draws each
@@ -269,7 +262,7 @@ struct WarpBoard {
                     break;
                 }
                 if (!bad) {
-                    bad = (eval_cells(agent, idx) & F_BAD) != 0;
+                    bad = eval_cells(agent, idx).bad;
                     if (!bad) return idx;
                 }
             }
