@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libagentgo_b200.so")
+LIB_PATH = os.environ.get("AGB_LIB", os.path.join(HERE, "libagentgo_b200.so"))
 
 EMPTY, BLACK, WHITE = 0, 1, 2
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
@@ -30,6 +30,7 @@ SYMBOLS = [
     "agb_get_board", "agb_check", "agb_count_score", "agb_export_state", "agb_playouts",
     "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
     "agb_set_allreduce", "agb_playouts_batch", "agb_genmove", "agb_measure_peaks",
+    "agb_debug_violations",
 ]
 
 
@@ -113,8 +114,14 @@ def lib():
                               C.POINTER(Stats)]
     l.agb_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    l.agb_debug_violations.restype = C.c_longlong
     _lib = l
     return l
+
+
+def debug_violations():
+    """Bounds violations counted by the AGB_CHECK_BOUNDS build (0 in the release build)."""
+    return int(lib().agb_debug_violations())
 
 
 def measure_peaks(device=0):

@@ -31,17 +31,21 @@ def _all_deps():
     return deps
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
+    """debug=True builds libagentgo_b200_dbg.so with -DAGB_CHECK_BOUNDS (checked shared-memory
+    indexing in the warp kernel); select it at run time with AGB_LIB=<path>."""
     deps = _all_deps()
-    if force or _stale(LIB, deps):
+    lib = LIB.replace(".so", "_dbg.so") if debug else LIB
+    if force or _stale(lib, deps):
         objs = []
-        objdir = os.path.join(HERE, "build")
+        objdir = os.path.join(HERE, "build", "dbg" if debug else "rel")
         os.makedirs(objdir, exist_ok=True)
         procs = []
         for src in SOURCES:
             obj = os.path.join(objdir, src + ".o")
             objs.append(obj)
-            cmd = [NVCC] + ARCH + COMMON + ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
+            cmd = [NVCC] + ARCH + COMMON + (["-DAGB_CHECK_BOUNDS"] if debug else []) + \
+                  ["-x", "cu", "-c", os.path.join(CSRC, src), "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -55,8 +59,10 @@ def build(force=False, verbose=False):
                 sys.stderr.write(out)
         if failed:
             raise RuntimeError("CUDA build failed")
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
+    if debug:
+        return lib
     gtp_src = os.path.join(CSRC, "gtp_main.cpp")
     if os.path.exists(gtp_src) and (force or _stale(GTP, deps + [LIB])):
         cmd = ["g++", "-O2", "-std=c++17", "-I", CSRC, "-I", INCLUDE, gtp_src,
@@ -67,4 +73,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug="--debug" in sys.argv))

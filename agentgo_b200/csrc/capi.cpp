@@ -7,6 +7,7 @@
 
 #include "agentgo_b200.h"
 #include "engine.h"
+#include "kernel_args.h"
 
 using agb::Engine;
 
@@ -185,5 +186,7 @@ int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_ro
     return h->e->genmove(colour, P_per_candidate, P_root, seed_base, row, col, is_pass, stats);
     AGB_GUARD_END(h)
 }
+
+long long agb_debug_violations(void) { return (long long)agb::debug_violations(); }
 
 }  /* extern "C" */

@@ -61,6 +61,8 @@ struct LaunchInfo {
 // host helpers of the warp kernel's device layout (playout_warp.cu)
 void to_padded(const Position& p, PaddedPosition* out);
 void build_jump18(const RngParams& prm, JumpTable* out);
+// bounds violations counted by the AGB_CHECK_BOUNDS build of the warp kernel (0 in release)
+unsigned long long debug_violations();
 
 // thread-per-playout kernel (playout_thread.cu)
 cudaError_t launch_playout_thread(int n, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info);

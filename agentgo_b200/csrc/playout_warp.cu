@@ -41,6 +41,28 @@ namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kBorder = 3;
 
+// Shared-memory array view.  In the AGB_CHECK_BOUNDS build (agentgo_b200/build.py --debug; the
+// pool has no compute-sanitizer) every index is checked and violations are counted in
+// g_bounds_violations, which agb_debug_violations() returns; release builds index directly.
+#ifdef AGB_CHECK_BOUNDS
+__device__ unsigned long long g_bounds_violations;
+template <typename T>
+struct SmemArr {
+    T* p;
+    int n;
+    __device__ __forceinline__ T& operator[](int i) const {
+        if ((unsigned)i >= (unsigned)n) { atomicAdd(&g_bounds_violations, 1ull); i = 0; }
+        return p[i];
+    }
+};
+#else
+template <typename T>
+struct SmemArr {
+    T* p;
+    __device__ __forceinline__ T& operator[](int i) const { return p[i]; }
+};
+#endif
+
 __device__ __forceinline__ int fA(uint32_t w) { return (int)(w & 1023u); }
 __device__ __forceinline__ int fB(uint32_t w) { return (int)((w >> 10) & 1023u); }
 __device__ __forceinline__ int fCol(uint32_t w) { return (int)((w >> 20) & 3u); }
@@ -54,9 +76,9 @@ struct WarpBoard {
     static constexpr int W = N + 2;
     static constexpr int NP = W * W;
     static constexpr int NN = N * N;
-    uint32_t* w0;        // A | B<<10 | colour<<20 | reserve<<22   (field meaning: board_ops.h)
-    uint32_t* w1;        // hp | tail<<16 at root stones
-    uint16_t* scratch;   // NN entries: compacted list of empty points (complex mode)
+    SmemArr<uint32_t> w0;        // A | B<<10 | colour<<20 | reserve<<22   (field meaning: board_ops.h)
+    SmemArr<uint32_t> w1;        // hp | tail<<16 at root stones
+    SmemArr<uint16_t> scratch;   // NN entries: compacted list of empty points (complex mode)
     int lane;
     int off_nb;          // offset of this lane's orthogonal neighbour (dir = lane & 3: up, left, down, right)
     int off_dg;          // offset of this lane's diagonal
@@ -396,9 +418,13 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     WB bd;
-    bd.w0 = smem + (size_t)warp * BoardWords<N>::value;
-    bd.w1 = bd.w0 + WB::NP;
-    bd.scratch = reinterpret_cast<uint16_t*>(bd.w1 + WB::NP);
+    uint32_t* base = smem + (size_t)warp * BoardWords<N>::value;
+    bd.w0.p = base;
+    bd.w1.p = base + WB::NP;
+    bd.scratch.p = reinterpret_cast<uint16_t*>(base + 2 * WB::NP);
+#ifdef AGB_CHECK_BOUNDS
+    bd.w0.n = WB::NP; bd.w1.n = WB::NP; bd.scratch.n = WB::NN;
+#endif
     bd.init_lane(lane);
 
     unsigned long long moves = 0, draws = 0;
@@ -508,6 +534,16 @@ cudaError_t launch_w(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchIn
 }
 
 }  // namespace
+
+unsigned long long debug_violations() {
+#ifdef AGB_CHECK_BOUNDS
+    unsigned long long v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_bounds_violations, sizeof(v)) != cudaSuccess) return ~0ull;
+    return v;
+#else
+    return 0;
+#endif
+}
 
 // Host side of the padded layout: re-index a Position (board_ops.h) into a PaddedPosition.
 void to_padded(const Position& p, PaddedPosition* out) {

@@ -212,6 +212,10 @@ int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_ro
 int agb_measure_peaks(int device, double* int_ops_per_s, double* int_ops_per_s_alu_only,
                       double* smem_bytes_per_s, int* sm_count);
 
+/* Shared-memory bounds violations counted since load by the AGB_CHECK_BOUNDS build of the
+ * kernels (`python -m agentgo_b200.build --debug`); always 0 in the release build.          */
+long long agb_debug_violations(void);
+
 /* ---- the seed contract (shared verbatim by oracle and kernels) --------- */
 static inline uint32_t agb_playout_seed(uint64_t seed_base, uint32_t position_id,
                                         uint32_t candidate_idx, uint64_t playout_idx) {
