@@ -131,11 +131,16 @@ struct WarpBoard {
     // checkSuicide/Kill/Survive/Dying/Chase/TrueEye/Compete (Board.cpp:480-755).
     //   bad     = dying | true eye | suicide | ko   (the filter of both sampling phases)
     //   reserve = true eye | suicide | ko           (complex mode: no checkDying, :425-427)
-    // Force-inlined at three call sites; each site only reads the fields it needs, so the
-    // compiler drops the rest (complex mode needs neither the friend sums nor survive/chase).
+    // Force-inlined at three call sites.  MODE selects what is computed, because the warp-sync
+    // shuffles and ballots have side effects the compiler will not remove on its own:
+    //   kEvalAll     neighbourhood phase: everything
+    //   kEvalBad     rejection phase: `bad` only (no survive / chase: no fmin, fcap, eatari)
+    //   kEvalReserve complex mode: `reserve` only (additionally no friend sum)
     struct Eval {
         bool empty, kill, survive, chase, bad, reserve;
     };
+    enum { kEvalAll = 0, kEvalBad = 1, kEvalReserve = 2 };
+    template <int MODE>
     __device__ __forceinline__ Eval eval_cells(int agent, int cidx) const {
         const unsigned nib = 15u << (lane & ~3);                    // this cell's four lanes
         const uint32_t wc = w0[cidx];
@@ -156,18 +161,25 @@ struct WarpBoard {
 
         const int n_empty = __popc(__ballot_sync(kFull, ncol == 0) & nib);
         const bool ecap = (__ballot_sync(kFull, enemy && left == 0) & nib) != 0;
-        const bool eatari = (__ballot_sync(kFull, enemy && left == 1) & nib) != 0;
-        const bool fcap = (__ballot_sync(kFull, frnd && left == 0) & nib) != 0;
         const bool fsafe = (__ballot_sync(kFull, frnd && left > 0) & nib) != 0;
-        int fsum = (frnd && first) ? left : 0;
-        fsum += __shfl_xor_sync(kFull, fsum, 1);
-        fsum += __shfl_xor_sync(kFull, fsum, 2);
-        int fmin = frnd ? hp : 9999;
-        fmin = min(fmin, __shfl_xor_sync(kFull, fmin, 1));
-        fmin = min(fmin, __shfl_xor_sync(kFull, fmin, 2));
-        const int tot = n_empty + fsum;
         const bool suicide = n_empty == 0 && !ecap && !fsafe;       // Board.cpp:480-524
-        const bool dying = !ecap && tot == 1;                       // :628-679
+        bool dying = false, survive = false, chase = false;
+        if (MODE != kEvalReserve) {
+            int fsum = (frnd && first) ? left : 0;
+            fsum += __shfl_xor_sync(kFull, fsum, 1);
+            fsum += __shfl_xor_sync(kFull, fsum, 2);
+            const int tot = n_empty + fsum;
+            dying = !ecap && tot == 1;                              // :628-679
+            if (MODE == kEvalAll) {
+                const bool eatari = (__ballot_sync(kFull, enemy && left == 1) & nib) != 0;
+                const bool fcap = (__ballot_sync(kFull, frnd && left == 0) & nib) != 0;
+                int fmin = frnd ? hp : 9999;
+                fmin = min(fmin, __shfl_xor_sync(kFull, fmin, 1));
+                fmin = min(fmin, __shfl_xor_sync(kFull, fmin, 2));
+                survive = fcap && (ecap || tot > fmin);             // :565-626
+                chase = eatari && tot > 1;                          // :681-733
+            }
+        }
 
         // Board::checkTrueEye, :735-751 — lane `dir` also looks at one diagonal; a cell is on the
         // edge iff one of its orthogonal neighbours is a border cell
@@ -181,8 +193,8 @@ struct WarpBoard {
         Eval e;
         e.empty = fCol(wc) == 0;
         e.kill = ecap;                                              // :526-563
-        e.survive = fcap && (ecap || tot > fmin);                   // :565-626
-        e.chase = eatari && tot > 1;                                // :681-733
+        e.survive = survive;
+        e.chase = chase;
         e.reserve = eye || suicide || ko;
         e.bad = e.reserve || dying;
         return e;
@@ -209,7 +221,7 @@ struct WarpBoard {
         for (int base = 0; base < n_e; base += 8) {
             const int k = base + (lane >> 2);
             const int idx = k < n_e ? (int)scratch[k] : 0;          // 0 is a border cell
-            const Eval f = eval_cells(agent, idx);
+            const Eval f = eval_cells<kEvalReserve>(agent, idx);
             const bool res = f.empty && f.reserve;
             if (res && (lane & 3) == 0) w0[idx] |= (1u << 22);      // addReserve, :757-761
             reserved_total += __popc(__ballot_sync(kFull, res) & 0x11111111u);
@@ -248,7 +260,7 @@ struct WarpBoard {
         if (!complex_mode) {
             const int lm = agent == 1 ? last1 : last0;              // opponent's last move
             if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
-                const Eval f = eval_cells(agent, lm + off_cell);
+                const Eval f = eval_cells<kEvalAll>(agent, lm + off_cell);
                 const bool ok = f.empty && !f.bad;
                 const unsigned K = __ballot_sync(kFull, ok && f.kill);
                 const unsigned S = __ballot_sync(kFull, ok && f.survive);
@@ -284,7 +296,7 @@ struct WarpBoard {
                     break;
                 }
                 if (!bad) {
-                    bad = eval_cells(agent, idx).bad;
+                    bad = eval_cells<kEvalBad>(agent, idx).bad;
                     if (!bad) return idx;
                 }
             }
