@@ -73,7 +73,7 @@ int Engine::create(const agb_config& cfg, Engine** out, std::string* err) {
     {
         JumpTable* jt = new JumpTable;
         RngParams prm = {h->cfg.mat1, h->cfg.mat2, h->cfg.tmat};
-        build_jump18(prm, jt);
+        build_jump(prm, jump_steps(), jt);
         e = cudaMalloc(&h->d_jump_, sizeof(JumpTable));
         if (e == cudaSuccess) e = cudaMemcpy(h->d_jump_, jt, sizeof(JumpTable), cudaMemcpyHostToDevice);
         delete jt;
@@ -141,7 +141,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     memset(&a, 0, sizeof(a));
     a.starts = (const Position*)d_starts_;
     a.pstarts = (const PaddedPosition*)d_starts_;
-    a.jump18 = (const JumpTable*)d_jump_;
+    a.jump = (const JumpTable*)d_jump_;
     a.descs = (const StartDesc*)d_descs_;
     a.n_starts = S;
     a.P = P;

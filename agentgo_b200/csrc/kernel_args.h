@@ -21,9 +21,9 @@ struct PaddedPosition {
     int16_t head, stones, ko_key_col, ko_idx, last[2], ending, pad;
 };
 
-// GF(2) jump-ahead table of TinyMT32: T^18 split by state nibble.  jump[l*16 + v] is the image
-// of state nibble l (bits 4l..4l+3 of s0|s1|s2|s3) having value v; the new state is the XOR of
-// the 32 selected entries.
+// GF(2) jump-ahead table of TinyMT32: T^k split by state nibble (k = jump_steps(), the number of
+// draws each lane generates per ring refill).  e[l*16 + v] is the image of state nibble l (bits
+// 4l..4l+3 of s0|s1|s2|s3) having value v; the new state is the XOR of the 32 selected entries.
 struct JumpTable {
     uint4 e[32 * 16];
 };
@@ -35,7 +35,7 @@ struct JumpTable {
 struct KernelArgs {
     const Position* starts;     // [n_starts] device (thread kernel)
     const PaddedPosition* pstarts;  // [n_starts] device (warp kernel)
-    const JumpTable* jump18;    // device
+    const JumpTable* jump;      // device
     const StartDesc* descs;     // [n_starts] device
     int32_t n_starts;
     int64_t P;
@@ -60,7 +60,8 @@ struct LaunchInfo {
 
 // host helpers of the warp kernel's device layout (playout_warp.cu)
 void to_padded(const Position& p, PaddedPosition* out);
-void build_jump18(const RngParams& prm, JumpTable* out);
+int jump_steps();
+void build_jump(const RngParams& prm, int steps, JumpTable* out);
 // bounds violations counted by the AGB_CHECK_BOUNDS build of the warp kernel (0 in release)
 unsigned long long debug_violations();
 

@@ -11,20 +11,28 @@
 //    same scalar code on the same shared-memory words (same address, same value), so there is
 //    no divergence and no intra-warp communication.
 //  * The policy's predicates are evaluated LANE-PARALLEL: lane = (cell, direction) with
-//    8 cells x 4 directions = 32 lanes.  In the neighbourhood phase of Board::getRandomPiece
-//    (Board.cpp:354-380) the 8 cells are the 3x3 block around the opponent's last move (its
-//    centre is occupied by precondition), evaluated ONCE per move into three 8-bit masks
-//    (kill / survive / chase, already filtered by dying / true eye / suicide / ko).  The
-//    reference's 9-iteration loop then degenerates to two RNG draws + a bit test per
-//    iteration, consuming exactly the reference's draw sequence (the predicates are pure
-//    functions of the state, which does not change inside the loop).
-//  * When all three masks are empty (75 % of the moves) none of the 18 draws can be accepted;
-//    the generator is advanced by 18 steps at once: TinyMT32's transition is linear over GF(2),
-//    so T^18 is applied as 32 per-lane nibble-table lookups (one LDG.128 per lane) folded by
-//    four redux.xor — about a dozen instructions instead of 18 x 12.
+//    8 cells x 4 directions = 32 lanes (eval_cells).
+//  * RANDOM NUMBERS ARE DECOUPLED FROM THEIR CONSUMPTION.  The reference consumes one serial
+//    rand() stream per playout; stepping one TinyMT32 in all 32 lanes costs 20 instructions per
+//    draw with one useful lane (it was 35 % of the kernel).  Instead each warp keeps a ring of
+//    1 024 pre-generated rand() values in shared memory.  A refill produces the next 512: the
+//    transition of TinyMT32 is linear over GF(2), so T^16 is applied 32 times as a per-lane
+//    nibble-table lookup (one LDG.128) folded by four redux.xor, giving every lane the start
+//    state of its own 16-draw segment, which it then generates by itself: ~1.8 instructions
+//    per draw.  Draw number p of a playout always lands in ring[p & 1023], so the stream the
+//    policy sees is exactly the reference's.
+//  * With the draws in shared memory both sampling loops of Board::getRandomPiece
+//    (Board.cpp:354-406) become lane-parallel too: they consume two draws per iteration
+//    whatever happens inside, and their predicates are pure functions of a state that does not
+//    change inside the loop, so lane j examines iteration j.  Neighbourhood phase: the 8 cells
+//    around the opponent's last move (the centre is occupied by precondition) are evaluated
+//    once into three 8-bit masks (kill / survive / chase, filtered by dying / true eye /
+//    suicide / ko); lanes 0..8 test their iteration against them; empty masks (75 % of the
+//    moves) just advance the read position by 18.  Rejection phase: 32 (row, col) pairs per
+//    round, the empty ones are evaluated in draw order, 8 per eval_cells call; the 100th draw
+//    is never accepted (Board.cpp:402-405).
 //  * Clone, scoring and the complex-mode legality pass are strided over the lanes; complex mode
 //    first compacts the empty points with ballots.
-//  * The RNG (TinyMT32, one stream per playout) is warp-uniform in registers.
 //
 // The code is written for a SMALL INSTRUCTION FOOTPRINT: 32 warps per SM sit at 32 different
 // program counters, and the first version of this kernel (every helper force-inlined, both
@@ -88,8 +96,18 @@ struct WarpBoard {
     int ko_key;          // exist_compete ? compete colour<<16 | idx : -1
     int last0, last1;    // last_move[colour-1] as idx, -1 = none
     int ending;          // game_ending
-    TinyMT mt;
-    uint32_t draws;
+    // --- random numbers: a ring of pre-generated rand() values (see refill) ---
+    SmemArr<uint16_t> ring;      // kRing entries, entry (p & (kRing-1)) holds draw number p of this playout
+    uint32_t g0, g1, g2, g3;     // generator state at draw number gen_end (warp-uniform)
+    uint32_t pos;                // next draw to be consumed = rand() calls made so far
+    uint32_t gen_end;            // draws [pos, gen_end) are in the ring
+
+    static constexpr int kRing = 1024;
+    static constexpr int kSeg = 16;                 // draws generated per lane per refill
+    static constexpr int kRefill = 32 * kSeg;       // 512 draws per refill
+    // One move consumes at most 18 (neighbourhood) + 200 (rejection) + 1 (complex) draws and the
+    // lane-parallel phases never read past that, so this much is made available before each move.
+    static constexpr int kLookahead = 224;
 
     __device__ __forceinline__ void init_lane(int l) {
         lane = l;
@@ -101,28 +119,45 @@ struct WarpBoard {
         off_cell = (cc / 3 - 1) * W + (cc % 3 - 1);
     }
 
-    __device__ __forceinline__ uint32_t rand15(const RngParams& p) {
-        mt.next_state(p.mat1, p.mat2);
-        return mt.temper(p.tmat) >> 17;
-    }
-    // rand() % M for a 15-bit value and a small constant M: one IMAD.HI and one IMAD
+    // rand() number pos + i (i < kLookahead), without consuming it
+    __device__ __forceinline__ uint32_t peek(uint32_t i) const { return ring[(pos + i) & (kRing - 1)]; }
+    // v % M for a 15-bit value and a small constant M: one IMAD.HI and one IMAD
     // (q = floor(v * ceil(2^32 / M) / 2^32) is exact for v < 2^15)
     template <uint32_t M>
-    __device__ __forceinline__ uint32_t rand_mod(const RngParams& p) {
-        const uint32_t v = rand15(p);
+    __device__ __forceinline__ static uint32_t mod_small(uint32_t v) {
         const uint32_t q = __umulhi(v, (uint32_t)((0x100000000ull + M - 1) / M));
         return v - q * M;
     }
 
-    // advance the generator by 18 steps (values not needed): s' = T^18 s over GF(2)
-    __device__ __forceinline__ void jump18(const JumpTable* __restrict__ jt) {
-        const uint32_t word = lane < 16 ? (lane < 8 ? mt.s0 : mt.s1) : (lane < 24 ? mt.s2 : mt.s3);
-        const uint32_t nib = (word >> ((lane & 7) * 4)) & 15u;
-        const uint4 t = __ldg(&jt->e[lane * 16 + nib]);
-        mt.s0 = __reduce_xor_sync(kFull, t.x);
-        mt.s1 = __reduce_xor_sync(kFull, t.y);
-        mt.s2 = __reduce_xor_sync(kFull, t.z);
-        mt.s3 = __reduce_xor_sync(kFull, t.w);
+    // Generate the next kRefill draws of this playout's TinyMT32 stream into the ring.
+    // All 32 lanes used to step the one generator redundantly (20 instructions per draw, a
+    // quarter of the kernel); here the serial part is only the 32 segment-start states: the
+    // transition is linear over GF(2), so T^16 is applied as a per-lane nibble-table lookup
+    // (LDG.128) folded by four redux.xor, and then every lane generates its own 16 draws.
+    __device__ __forceinline__ void refill(const RngParams& prm, const JumpTable* __restrict__ jt) {
+        TinyMT mine;
+        mine.s0 = g0; mine.s1 = g1; mine.s2 = g2; mine.s3 = g3;
+        const bool lo16 = lane < 16, lo8 = (lane & 8) == 0;
+        const uint32_t sh = (lane & 7) * 4;
+        const uint4* __restrict__ row = &jt->e[lane * 16];
+#pragma unroll 1
+        for (int l = 0; l < 32; l++) {
+            if (lane == l) { mine.s0 = g0; mine.s1 = g1; mine.s2 = g2; mine.s3 = g3; }
+            const uint32_t word = lo16 ? (lo8 ? g0 : g1) : (lo8 ? g2 : g3);
+            const uint4 t = __ldg(&row[(word >> sh) & 15u]);
+            g0 = __reduce_xor_sync(kFull, t.x);
+            g1 = __reduce_xor_sync(kFull, t.y);
+            g2 = __reduce_xor_sync(kFull, t.z);
+            g3 = __reduce_xor_sync(kFull, t.w);
+        }
+        const uint32_t base = gen_end + (uint32_t)lane * kSeg;
+#pragma unroll 2
+        for (int j = 0; j < kSeg; j++) {
+            mine.next_state(prm.mat1, prm.mat2);
+            ring[(base + j) & (kRing - 1)] = (uint16_t)(mine.temper(prm.tmat) >> 17);
+        }
+        gen_end += kRefill;
+        __syncwarp();
     }
 
     // Lane-parallel evaluation of up to 8 points at once: lane = 4*cell + dir evaluates
@@ -203,7 +238,7 @@ struct WarpBoard {
     // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags): the empty points
     // are compacted with ballots, then evaluated 8 per round with eval_cells; the ordered walk
     // that maps rnd to a point follows the empty list and is warp-uniform.
-    __device__ __forceinline__ int random_piece_complex(const RngParams& prm, int agent) {
+    __device__ __forceinline__ int random_piece_complex(int agent) {
         const int spaces = NN - stones;
         if (spaces == 0) return -1;
         int n_e = 0;
@@ -230,8 +265,8 @@ struct WarpBoard {
         const int range = spaces - reserved_total;
         int pick = -1;
         if (range != 0) {
-            draws++;
-            int rnd = (int)(rand15(prm) % (uint32_t)range);
+            int rnd = (int)(peek(0) % (uint32_t)range);
+            pos++;
 #pragma unroll 1
             for (int idx = head;;) {
                 const uint32_t w = w0[idx];
@@ -250,8 +285,12 @@ struct WarpBoard {
         return pick;
     }
 
-    // Board::getRandomPiece, Board.cpp:341-411; returns the (padded) point or -1 (pass)
-    __device__ __forceinline__ int random_piece(const RngParams& prm, const JumpTable* jt, int agent) {
+    // Board::getRandomPiece, Board.cpp:341-411; returns the (padded) point or -1 (pass).
+    // Both sampling loops of the reference consume two rand() per iteration whatever happens
+    // inside, and the predicates are pure functions of a state that does not change inside the
+    // loops, so lane j can examine iteration j directly from the ring: the first accepted
+    // iteration wins and exactly its draws (and those before it) are consumed.
+    __device__ __forceinline__ int random_piece(int agent) {
         bool complex_mode = false;
         if (ending) {                                               // :348-351
             if (stones <= kEndingStones) ending = 0;
@@ -265,43 +304,59 @@ struct WarpBoard {
                 const unsigned K = __ballot_sync(kFull, ok && f.kill);
                 const unsigned S = __ballot_sync(kFull, ok && f.survive);
                 const unsigned C = __ballot_sync(kFull, ok && f.chase);
-                draws += 18;
-                if ((K | S | C) == 0) {
-                    // no cell can be accepted: the loop runs its 9 iterations, 2 draws each
-                    jump18(jt);
-                } else {
-#pragma unroll 1
-                    for (int k = 0; k < 9; k++) {
-                        const uint32_t a = rand_mod<3>(prm);
-                        const uint32_t b = rand_mod<3>(prm);
-                        const uint32_t c9 = a * 3u + b;
-                        const uint32_t c8 = c9 - (c9 > 4u);
-                        const unsigned m = K | (k < 6 ? S : 0u) | (k < 4 ? C : 0u);
-                        if (c9 != 4 && ((m >> (4 * c8)) & 1u)) {    // centre (c9 == 4) is occupied
-                            draws -= 2 * (8 - k);
-                            return lm + (int)(a * W + b) - (W + 1);
-                        }
+                if ((K | S | C) != 0) {
+                    // lane k = iteration k of `for (k = 0; k < 9; k++)`
+                    const uint32_t a = mod_small<3>(peek(2 * lane));
+                    const uint32_t b = mod_small<3>(peek(2 * lane + 1));
+                    const uint32_t c9 = a * 3u + b;
+                    const uint32_t c8 = c9 - (c9 > 4u);
+                    const unsigned m = K | (lane < 6 ? S : 0u) | (lane < 4 ? C : 0u);
+                    const bool hit = lane < 9 && c9 != 4u && ((m >> (4 * c8)) & 1u);   // centre is occupied
+                    const unsigned hm = __ballot_sync(kFull, hit);
+                    if (hm) {
+                        const int k = __ffs(hm) - 1;
+                        pos += 2 * (k + 1);
+                        return lm + (int)__shfl_sync(kFull, a * W + b, k) - (W + 1);
                     }
                 }
+                pos += 18;      // nine iterations, two draws each, none accepted
             }
+            // rejection loop, :382-406: pairs count+1 .. count+B are examined in one round
 #pragma unroll 1
-            for (int count = 1;; count++) {                         // :382-406
-                draws += 2;
-                const uint32_t row = rand_mod<N>(prm);
-                const uint32_t cl = rand_mod<N>(prm);
+            for (int count = 0; count < kEndingThreshold;) {
+                const int B = min(32, kEndingThreshold - count);
+                const uint32_t row = mod_small<N>(peek(2 * lane));
+                const uint32_t cl = mod_small<N>(peek(2 * lane + 1));
                 const int idx = (int)(row * W + cl + (W + 1));
-                bool bad = fCol(w0[idx]) != 0;
-                if (count == kEndingThreshold) {                    // even if the 100th draw passed
-                    ending = 1;
-                    break;
+                // the 100th draw is never accepted (:402-405)
+                const bool can = lane < B && count + lane + 1 != kEndingThreshold && fCol(w0[idx]) == 0;
+                unsigned cand = __ballot_sync(kFull, can);
+                // evaluate the empty candidates in draw order, 8 per round
+#pragma unroll 1
+                while (cand) {
+                    const int rank = __popc(cand & ((1u << lane) - 1u));
+                    const bool mine = ((cand >> lane) & 1u) && rank < 8;
+                    if (mine) scratch[rank] = (uint16_t)(idx | (lane << 9));
+                    __syncwarp();
+                    const int ncand = min(8, __popc(cand));
+                    const int cell = lane >> 2;
+                    const uint32_t entry = cell < ncand ? scratch[cell] : 0u;     // 0 = a border cell
+                    const Eval e = eval_cells<kEvalBad>(agent, (int)(entry & 511u));
+                    const unsigned good = __ballot_sync(kFull, cell < ncand && !e.bad);
+                    if (good) {
+                        const uint32_t win = __shfl_sync(kFull, entry, __ffs(good) - 1);
+                        pos += 2 * ((win >> 9) + 1);
+                        return (int)(win & 511u);
+                    }
+                    cand &= ~__ballot_sync(kFull, mine);
+                    __syncwarp();
                 }
-                if (!bad) {
-                    bad = eval_cells<kEvalBad>(agent, idx).bad;
-                    if (!bad) return idx;
-                }
+                pos += 2 * B;
+                count += B;
             }
+            ending = 1;
         }
-        return random_piece_complex(prm, agent);
+        return random_piece_complex(agent);
     }
 
     // Board::killSetNode, Board.cpp:293-339 (warp-uniform)
@@ -416,11 +471,13 @@ struct WarpBoard {
     }
 };
 
-// per-warp shared memory: w0[NP], w1[NP], scratch[NN] (16 bit), rounded to 32 words
+// per-warp shared memory in words: w0[NP], w1[NP], scratch[NN] (16 bit) rounded to 32 words,
+// then the ring of kRing 16-bit draws
 template <int N>
 struct BoardWords {
     static constexpr int NP = (N + 2) * (N + 2);
-    static constexpr int value = ((2 * NP + (N * N + 1) / 2 + 31) / 32) * 32;
+    static constexpr int board = ((2 * NP + (N * N + 1) / 2 + 31) / 32) * 32;
+    static constexpr int value = board + WarpBoard<N>::kRing / 2;
 };
 
 template <int N, int WARPS, int BLOCKS_PER_SM>
@@ -434,8 +491,9 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
     bd.w0.p = base;
     bd.w1.p = base + WB::NP;
     bd.scratch.p = reinterpret_cast<uint16_t*>(base + 2 * WB::NP);
+    bd.ring.p = reinterpret_cast<uint16_t*>(base + BoardWords<N>::board);
 #ifdef AGB_CHECK_BOUNDS
-    bd.w0.n = WB::NP; bd.w1.n = WB::NP; bd.scratch.n = WB::NN;
+    bd.w0.n = WB::NP; bd.w1.n = WB::NP; bd.scratch.n = WB::NN; bd.ring.n = WB::kRing;
 #endif
     bd.init_lane(lane);
 
@@ -466,7 +524,8 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         bd.last0 = pos.last[0];
         bd.last1 = pos.last[1];
         bd.ending = pos.ending;
-        bd.draws = 0;
+        bd.pos = 0;
+        bd.gen_end = 0;
         __syncwarp();
         {
             // tinymt32_init (RFC 8682)
@@ -478,9 +537,11 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             if ((st[0] & 0x7fffffffu) == 0 && st[1] == 0 && st[2] == 0 && st[3] == 0) {
                 st[0] = 'T'; st[1] = 'I'; st[2] = 'N'; st[3] = 'Y';
             }
-            bd.mt.s0 = st[0]; bd.mt.s1 = st[1]; bd.mt.s2 = st[2]; bd.mt.s3 = st[3];
+            TinyMT t;
+            t.s0 = st[0]; t.s1 = st[1]; t.s2 = st[2]; t.s3 = st[3];
 #pragma unroll 1
-            for (int i = 0; i < 8; i++) bd.mt.next_state(a.rng.mat1, a.rng.mat2);
+            for (int i = 0; i < 8; i++) t.next_state(a.rng.mat1, a.rng.mat2);
+            bd.g0 = t.s0; bd.g1 = t.s1; bd.g2 = t.s2; bd.g3 = t.s3;
         }
 
         // pair loop of MyWorker::work (AgentGo.cpp:295-325) / testAvrgWin (:422-443), one move
@@ -491,7 +552,8 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
 #pragma unroll 1
         for (int t = 0;; t++) {
             const int colour = (t & 1) ? 3 - first : first;
-            const int r = bd.random_piece(a.rng, a.jump18, colour);
+            while (bd.gen_end - bd.pos < (uint32_t)WB::kLookahead) bd.refill(a.rng, a.jump);
+            const int r = bd.random_piece(colour);
             if (r >= 0) {
                 bd.put(colour, r);
                 mv++;
@@ -506,7 +568,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         __syncwarp();
         const int diff = fault ? -32768 : bd.score_diff(d.agent);
         moves += mv;
-        draws += bd.draws;
+        draws += bd.pos;
         played++;
         if (fault) faults++;
         if (lane == 0) {
@@ -581,15 +643,16 @@ void to_padded(const Position& p, PaddedPosition* out) {
     out->pad = 0;
 }
 
-// T^18 of TinyMT32 as a nibble table (see JumpTable): column b of T^18 is the state reached from
-// the unit vector e_b after 18 transitions (the transition is linear over GF(2)).
-void build_jump18(const RngParams& prm, JumpTable* out) {
+// T^steps of TinyMT32 as a nibble table (see JumpTable): column b of T^steps is the state reached
+// from the unit vector e_b after `steps` transitions (the transition is linear over GF(2)).
+int jump_steps() { return WarpBoard<19>::kSeg; }
+void build_jump(const RngParams& prm, int steps, JumpTable* out) {
     uint32_t col[128][4];
     for (int b = 0; b < 128; b++) {
         TinyMT t;
         t.s0 = t.s1 = t.s2 = t.s3 = 0;
         (b < 32 ? t.s0 : (b < 64 ? t.s1 : (b < 96 ? t.s2 : t.s3))) = 1u << (b & 31);
-        for (int i = 0; i < 18; i++) t.next_state(prm.mat1, prm.mat2);
+        for (int i = 0; i < steps; i++) t.next_state(prm.mat1, prm.mat2);
         col[b][0] = t.s0; col[b][1] = t.s1; col[b][2] = t.s2; col[b][3] = t.s3;
     }
     for (int l = 0; l < 32; l++)
