@@ -233,10 +233,12 @@ def run_b200(args):
     if os.path.exists(peaks_file):
         hbm_peak, hbm_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     mp = ag.measure_peaks(local_rank)
-    traffic = None
+    traffic, winst = None, None
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
-        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        pj = json.load(open(prof))
+        traffic = pj.get("dram_bytes_per_launch")
+        winst = pj.get("warp_instructions_per_playout")
     launch_ms = 1e3 * dev_total / K
     hbm_achieved = args.playouts * W_HBM_BYTES / (launch_ms * 1e-3) / 1e9
     roofline = {
@@ -253,6 +255,13 @@ def run_b200(args):
                  "frac": per_gpu_rate * W_SMEM_BYTES / mp["smem_bytes_per_s"],
                  "algorithmic_bytes_per_playout": W_SMEM_BYTES, "peak_source": "agb_measure_peaks, live"},
     }
+    if winst and clocks and clocks.get("sm_mhz"):
+        # issued side: warp-instructions per playout from ncu (profiles/), against 4 issue slots
+        # per clock per SM at the SM clock sampled during this run
+        peak_issue = mp["sm_count"] * 4 * clocks["sm_mhz"] * 1e6
+        roofline["issue_slots"] = {"achieved": per_gpu_rate * winst, "peak": peak_issue, "unit": "warp-instructions/s",
+                                   "frac": per_gpu_rate * winst / peak_issue, "warp_instructions_per_playout": winst,
+                                   "source": "ncu smsp__inst_executed.sum (profiles/roofline_traffic.json)"}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rates, info = cpu_reference(sample_seconds=args.cpu_seconds)

@@ -2,7 +2,7 @@
 """Aggregate tools/ncu_by_line.py output (all lines) by code region of playout_warp.cu."""
 import re, sys
 src = open('agentgo_b200/csrc/playout_warp.cu').read().splitlines()
-marks = [('eval_cells', 'uint32_t eval_cells('), ('complex', 'int random_piece_complex('), ('random_piece', 'int random_piece('),
+marks = [('refill', 'void refill('), ('eval_cells', 'Eval eval_cells('), ('complex', 'int random_piece_complex('), ('random_piece', 'int random_piece('),
          ('kill', 'void kill_string('), ('put', 'void put('), ('score', 'int score_diff('), ('kernel', 'playout_warp_kernel(const')]
 starts = []
 for name, pat in marks:
