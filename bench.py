@@ -35,6 +35,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_json_fd = 1
 METRIC = "19x19 playouts/sec"
 UNIT = "playouts/s"
 BOARD = 19
@@ -152,6 +153,10 @@ def run_reference(args):
 
 
 def run_b200(args):
+    # stdout must carry exactly ONE JSON line: libraries (NCCL prints its version banner) get stderr
+    global _json_fd
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
     import numpy as np
     import torch
     import agentgo_b200 as ag
@@ -276,7 +281,7 @@ def run_b200(args):
             "gpu_launches": launches_total, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "last_counts": {"wins": counts[0], "sum_pos": counts[1], "sum_neg": counts[2]},
             "impl": "b200"}
-    print(json.dumps(line))
+    os.write(_json_fd, (json.dumps(line) + "\n").encode())
     if tdist is not None:
         tdist.destroy_process_group()
     return 0
