@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("AGB_LIB", os.path.join(HERE, "libagentgo_b200.so"))
 EMPTY, BLACK, WHITE = 0, 1, 2
 KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
 ROOT_CANDIDATE = 0xFFFFFFFF
+AMAF_RANGE = 40
 CHECKS = {"suicide": 0, "kill": 1, "survive": 2, "dying": 3, "chase": 4,
           "true_eye": 5, "compete": 6, "no_sense": 7}
 STATUS = {0: "AGB_OK", -1: "AGB_ERR_INVALID", -2: "AGB_ERR_OCCUPIED", -3: "AGB_ERR_CUDA",
@@ -28,7 +29,7 @@ SYMBOLS = [
     "agb_default_config", "agb_create", "agb_destroy", "agb_last_error", "agb_version",
     "agb_device_count", "agb_boardsize", "agb_clear_board", "agb_play", "agb_pass",
     "agb_get_board", "agb_check", "agb_count_score", "agb_export_state", "agb_playouts",
-    "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
+    "agb_playouts_amaf", "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
     "agb_set_allreduce", "agb_playouts_batch", "agb_genmove", "agb_measure_peaks",
     "agb_debug_violations",
 ]
@@ -99,6 +100,8 @@ def lib():
     l.agb_export_state.argtypes = [vp, i32p, C.c_int]
     l.agb_playouts.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int64, C.c_int, C.c_uint64, C.c_uint32,
                                i64p, i64p, i64p, i16p, C.POINTER(Stats)]
+    l.agb_playouts_amaf.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int64, C.c_int, C.c_uint64, C.c_uint32,
+                                    i64p, i64p, i64p, i64p, C.POINTER(Stats)]
     l.agb_playouts_launch.argtypes = [vp, C.c_int, i16p, C.c_int, C.c_int64, C.c_int, C.c_uint64,
                                       C.c_uint32, C.c_int]
     l.agb_playouts_finish.argtypes = [vp, i64p, i64p, i64p, i16p, C.POINTER(Stats)]
@@ -266,6 +269,20 @@ class Engine:
         """-> (wins, sum_pos, sum_neg, diffs|None, stats) for this engine's shard."""
         self.playouts_launch(colour, cands, P, avrg_win, seed_base, position_id, want_diffs)
         return self.playouts_finish()
+
+    def playouts_amaf(self, colour, cands, P, avrg_win=0, seed_base=20151001, position_id=0):
+        """Candidate-mode playouts with AMAF first-play marks.
+        -> (wins, sum_pos, sum_neg, amaf int64 [2 which][2 sign][41 step][N*N], stats)"""
+        cands = list(cands)
+        Cn = len(cands)
+        rc = np.array(cands, dtype=np.int16).reshape(-1)
+        wins, sp, sn = (np.zeros(Cn, dtype=np.int64) for _ in range(3))
+        amaf = np.zeros((2, 2, AMAF_RANGE + 1, self.n * self.n), dtype=np.int64)
+        st = Stats()
+        self._chk(self._l.agb_playouts_amaf(self._h, colour, _p(rc, C.c_int16), Cn, P, avrg_win, seed_base,
+                                            position_id, _p(wins, C.c_int64), _p(sp, C.c_int64),
+                                            _p(sn, C.c_int64), _p(amaf, C.c_int64), C.byref(st)))
+        return wins, sp, sn, amaf, st.as_dict()
 
     def playouts_batch(self, positions, P, seed_base=20151001, first_position_id=0, want_diffs=False):
         """positions: list of (moves uint32 array, to_move)."""

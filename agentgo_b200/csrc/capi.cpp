@@ -159,6 +159,17 @@ int agb_playouts(agb_engine* h, int colour, const int16_t* cand_rc, int C, int64
     return agb_playouts_finish(h, wins, sum_pos, sum_neg, per_playout_diff, stats);
 }
 
+int agb_playouts_amaf(agb_engine* h, int colour, const int16_t* cand_rc, int C, int64_t P, int avrg_win,
+                      uint64_t seed_base, uint32_t position_id, int64_t* wins, int64_t* sum_pos,
+                      int64_t* sum_neg, int64_t* amaf, agb_stats* stats) {
+    if (!h || !amaf) return AGB_ERR_INVALID;
+    AGB_GUARD_BEGIN
+    int st = h->e->playouts_launch(colour, cand_rc, C, P, avrg_win, seed_base, position_id, false, true);
+    if (st) return st;
+    return h->e->finish(wins, sum_pos, sum_neg, nullptr, stats, amaf);
+    AGB_GUARD_END(h)
+}
+
 void* agb_counters_dev(agb_engine* h) { return h ? h->e->counters_dev() : nullptr; }
 void* agb_stream(agb_engine* h) { return h ? (void*)h->e->stream() : nullptr; }
 

@@ -92,7 +92,7 @@ Engine::~Engine() {
     cudaSetDevice(cfg.device);
     if (stream_) cudaStreamSynchronize(stream_);
     cudaFree(d_starts_); cudaFree(d_descs_); cudaFree(d_counters_); cudaFree(d_diffs_);
-    cudaFree(d_small_); cudaFree(d_jump_);
+    cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_amaf_);
     if (h_pinned_) cudaFreeHost(h_pinned_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -111,7 +111,7 @@ int Engine::ensure(void** ptr, size_t* cap, size_t bytes) {
 }
 
 int Engine::launch(const std::vector<Position>& starts, const std::vector<StartDesc>& descs, int64_t P,
-                   uint64_t seed_base, bool want_diffs, bool shard_units) {
+                   uint64_t seed_base, bool want_diffs, bool shard_units, bool want_amaf) {
     if (cfg.device < 0) return fail(AGB_ERR_CUDA, "engine was created without a CUDA device (device = -1); no CPU fallback");
     if (in_flight_) return fail(AGB_ERR_STATE, "a launch is already in flight");
     if (starts.empty() || starts.size() != descs.size() || P <= 0)
@@ -120,6 +120,13 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     const int S = (int)starts.size();
     int st;
     const bool thread_kernel = cfg.kernel == AGB_KERNEL_THREAD;
+    if (want_amaf && thread_kernel)
+        return fail(AGB_ERR_INVALID, "AMAF marks are implemented by the warp kernel only");
+    const size_t amaf_bytes = sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n());
+    if (want_amaf) {
+        if ((st = ensure(&d_amaf_, &cap_amaf_, amaf_bytes))) return st;
+        AGB_CUDA(cudaMemsetAsync(d_amaf_, 0, amaf_bytes, stream_));
+    }
     const size_t start_bytes = (thread_kernel ? sizeof(Position) : sizeof(PaddedPosition)) * (size_t)S;
     if ((st = ensure(&d_starts_, &cap_starts_, start_bytes))) return st;
     if ((st = ensure(&d_descs_, &cap_descs_, sizeof(StartDesc) * (size_t)S))) return st;
@@ -154,6 +161,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     a.stats = (unsigned long long*)d_small_ + 1;
     a.counters = (long long*)d_counters_;
     a.diffs = want_diffs ? (int16_t*)d_diffs_ : nullptr;
+    a.amaf = want_amaf ? (long long*)d_amaf_ : nullptr;
     a.rng.mat1 = cfg.mat1; a.rng.mat2 = cfg.mat2; a.rng.tmat = cfg.tmat;
     a.max_moves = cfg.max_moves;
 
@@ -166,11 +174,12 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     }
     in_flight_ = true;
-    n_starts_ = S; P_ = P; want_diffs_ = want_diffs; shard_units_ = shard_units;
+    n_starts_ = S; P_ = P; want_diffs_ = want_diffs; shard_units_ = shard_units; want_amaf_ = want_amaf;
     return AGB_OK;
 }
 
-int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats) {
+int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats,
+                   int64_t* amaf) {
     if (!in_flight_) return fail(AGB_ERR_STATE, "no launch in flight");
     in_flight_ = false;
     AGB_CUDA(cudaSetDevice(cfg.device));
@@ -186,6 +195,10 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
     if (allreduce_) {
         int r = allreduce_(allreduce_ctx_, d_counters_, 3 * S, (void*)stream_);
         if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
+        if (want_amaf_) {
+            r = allreduce_(allreduce_ctx_, d_amaf_, AGB_AMAF_WORDS(board.n()), (void*)stream_);
+            if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
+        }
     }
     // device time of the evaluation = kernel (+ collective), stream ordered
     AGB_CUDA(cudaEventRecord(ev1_, stream_));
@@ -195,6 +208,11 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
     AGB_CUDA(cudaMemcpyAsync(hs, d_small_, kSmallWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
     if (diffs && want_diffs_ && !(shard_units_ && cfg.shard_count > 1))
         AGB_CUDA(cudaMemcpyAsync(diffs, d_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P_, cudaMemcpyDeviceToHost, stream_));
+    if (amaf) {
+        if (!want_amaf_) return fail(AGB_ERR_STATE, "the launch in flight did not record AMAF marks");
+        AGB_CUDA(cudaMemcpyAsync(amaf, d_amaf_, sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n()),
+                                 cudaMemcpyDeviceToHost, stream_));
+    }
     AGB_CUDA(cudaStreamSynchronize(stream_));
     if (diffs && want_diffs_ && shard_units_ && cfg.shard_count > 1) {
         // only this shard's entries are defined on the device; leave the others untouched
@@ -223,7 +241,8 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
 }
 
 int Engine::playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P, int avrg_win,
-                            uint64_t seed_base, uint32_t position_id, bool want_diffs) {
+                            uint64_t seed_base, uint32_t position_id, bool want_diffs, bool want_amaf) {
+    if (want_amaf && C == 0) return fail(AGB_ERR_INVALID, "AMAF marks exist in candidate mode only");
     if (colour != AGB_BLACK && colour != AGB_WHITE) return fail(AGB_ERR_INVALID, "bad colour");
     if (C < 0 || (C > 0 && !cand_rc) || P <= 0) return fail(AGB_ERR_INVALID, "bad candidates or P");
     const int n = board.n();
@@ -246,7 +265,7 @@ int Engine::playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P
             descs.push_back(d);
         }
     }
-    return launch(starts, descs, P, seed_base, want_diffs, true);
+    return launch(starts, descs, P, seed_base, want_diffs, true, want_amaf);
 }
 
 int Engine::playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t seed_base,

@@ -30,12 +30,14 @@ public:
 
     // general launch: starts x P playouts, ids sharded by g % shard_count (by_unit) or all local
     int launch(const std::vector<Position>& starts, const std::vector<StartDesc>& descs, int64_t P,
-               uint64_t seed_base, bool want_diffs, bool shard_units);
+               uint64_t seed_base, bool want_diffs, bool shard_units, bool want_amaf = false);
     // waits, copies counters (and diffs) out.  Buffers are [n_starts] / [n_starts*P].
-    int finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats);
+    // amaf: [AGB_AMAF_WORDS(n)] or nullptr; only valid after a launch with want_amaf
+    int finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats,
+               int64_t* amaf = nullptr);
 
     int playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P, int avrg_win,
-                        uint64_t seed_base, uint32_t position_id, bool want_diffs);
+                        uint64_t seed_base, uint32_t position_id, bool want_diffs, bool want_amaf = false);
     int playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t seed_base,
                        uint32_t first_position_id, int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
                        int16_t* diffs, agb_stats* stats);
@@ -62,6 +64,7 @@ private:
     void* d_counters_ = nullptr; size_t cap_counters_ = 0;
     void* d_diffs_ = nullptr; size_t cap_diffs_ = 0;
     void* d_small_ = nullptr;            // work counter + stats
+    void* d_amaf_ = nullptr; size_t cap_amaf_ = 0;   // AMAF table [2][2][41][NN] int64
     void* h_pinned_ = nullptr; size_t cap_pinned_ = 0;
 
     // state of the launch in flight
@@ -70,6 +73,7 @@ private:
     int64_t P_ = 0;
     bool want_diffs_ = false;
     bool shard_units_ = false;
+    bool want_amaf_ = false;
     LaunchInfo info_ = {0, 0, 0, ""};
     AllreduceFn allreduce_ = nullptr;
     void* allreduce_ctx_ = nullptr;

@@ -45,6 +45,7 @@ struct KernelArgs {
     unsigned long long* work_counter;   // device, zeroed before launch
     long long* counters;        // device [3][n_starts]: wins | sum_pos | sum_neg
     int16_t* diffs;             // device [n_starts*P] or nullptr
+    long long* amaf;            // device [2 which][2 sign][41 step][N*N] or nullptr (AMAF marks, warp kernel)
     unsigned long long* stats;  // device [4]: moves, rng draws, faults, playouts
     RngParams rng;
     int32_t max_moves;

@@ -48,6 +48,7 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kBorder = 3;
+constexpr int kAmafRange = 40;      // AMAF_RANGE, GoContest/AgentGo.h:16
 
 // Shared-memory array view.  In the AGB_CHECK_BOUNDS build (agentgo_b200/build.py --debug; the
 // pool has no compute-sanitizer) every index is checked and violations are counted in
@@ -478,16 +479,22 @@ struct BoardWords {
     static constexpr int NP = (N + 2) * (N + 2);
     static constexpr int board = ((2 * NP + (N * N + 1) / 2 + 31) / 32) * 32;
     static constexpr int value = board + WarpBoard<N>::kRing / 2;
+    static constexpr int kAmafLog = 80;                     // first plays with cstep <= 40: at most 78
+    static constexpr int value_amaf = value + kAmafLog / 2;
 };
 
-template <int N, int WARPS, int BLOCKS_PER_SM>
+// AMAF = true additionally records the first-play marks of MyWorker::work (AgentGo.cpp:289-290,
+// 304,319) and accumulates KernelArgs::amaf (:329-338); candidate mode only.
+template <int N, int WARPS, int BLOCKS_PER_SM, bool AMAF>
 __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel(const KernelArgs a) {
     extern __shared__ uint32_t smem[];
     typedef WarpBoard<N> WB;
+    constexpr int kWarpWords = AMAF ? BoardWords<N>::value_amaf : BoardWords<N>::value;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     WB bd;
-    uint32_t* base = smem + (size_t)warp * BoardWords<N>::value;
+    uint32_t* base = smem + (size_t)warp * kWarpWords;
+    uint16_t* amaf_log = reinterpret_cast<uint16_t*>(base + BoardWords<N>::value);   // AMAF only
     bd.w0.p = base;
     bd.w1.p = base + WB::NP;
     bd.scratch.p = reinterpret_cast<uint16_t*>(base + 2 * WB::NP);
@@ -549,6 +556,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         const int first = d.first;
         bool first_moved = true, fault = false;
         uint32_t mv = 0;
+        int n_log = 0;
 #pragma unroll 1
         for (int t = 0;; t++) {
             const int colour = (t & 1) ? 3 - first : first;
@@ -557,6 +565,20 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             if (r >= 0) {
                 bd.put(colour, r);
                 mv++;
+                if (AMAF) {
+                    // mark[r] / mark2[r] = cstep of the FIRST play of that side at r (:304,:319);
+                    // cstep is 2 in the first pair (:293,:297); only cstep <= AMAF_RANGE is ever used
+                    const int cstep = 2 + (t >> 1);
+                    if (cstep <= kAmafRange) {
+                        const uint32_t key = (uint32_t)r | (colour == d.agent ? 512u : 0u);
+                        bool dup = false;
+                        for (int b0 = 0; b0 < n_log; b0 += 32) {
+                            const uint32_t e = b0 + lane < n_log ? amaf_log[b0 + lane] : 0xffffu;
+                            dup |= __ballot_sync(kFull, (e & 1023u) == key) != 0;
+                        }
+                        if (!dup) { amaf_log[n_log] = (uint16_t)(key | ((uint32_t)cstep << 10)); n_log++; }
+                    }
+                }
             } else {                                                // Board::pass, Board.cpp:200-203
                 bd.ko_key = -1;
                 if (colour == 1) bd.last0 = -1; else bd.last1 = -1;
@@ -571,6 +593,30 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         draws += bd.pos;
         played++;
         if (fault) faults++;
+        if (AMAF && !fault) {
+            // :329-338 — point q counts for the agent table when the agent's first play there has
+            // cstep <= 40, else for the enemy table when the enemy's has (the `else if`)
+            __syncwarp();
+            const int w = diff - d.avrg_win;
+            uint32_t agent_bits = 0;                // bit (q & 31) of lane (q >> 5): agent marked q
+            for (int k = 0; k < n_log; k++) {
+                const uint32_t e = amaf_log[k];
+                if ((e & 512u) && lane == (int)((e & 511u) >> 5)) agent_bits |= 1u << (e & 31u);
+            }
+            for (int b0 = 0; b0 < n_log; b0 += 32) {
+                const bool valid = b0 + lane < n_log;
+                const uint32_t e = valid ? amaf_log[b0 + lane] : 0u;
+                const uint32_t q = e & 511u;
+                const bool is_agent = (e & 512u) != 0;
+                const bool agent_marked = (__shfl_sync(kFull, agent_bits, (int)(q >> 5)) >> (q & 31u)) & 1u;
+                if (valid && w != 0 && (is_agent || !agent_marked)) {
+                    const uint32_t row = q / WB::W - 1, col = q % WB::W - 1;
+                    const uint32_t slot = ((is_agent ? 0u : 2u) + (w < 0 ? 1u : 0u)) * (kAmafRange + 1) + (e >> 10);
+                    atomicAdd((unsigned long long*)&a.amaf[(size_t)slot * WB::NN + row * N + col],
+                              (unsigned long long)(long long)w);
+                }
+            }
+        }
         if (lane == 0) {
             if (a.diffs) a.diffs[g] = (int16_t)diff;
             if (!fault) {
@@ -593,17 +639,17 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
     }
 }
 
-template <int N, int WARPS, int BLOCKS_PER_SM>
+template <int N, int WARPS, int BLOCKS_PER_SM, bool AMAF>
 cudaError_t launch_w(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    const size_t smem = (size_t)WARPS * BoardWords<N>::value * sizeof(uint32_t);
-    cudaError_t e = cudaFuncSetAttribute(playout_warp_kernel<N, WARPS, BLOCKS_PER_SM>,
+    const size_t smem = (size_t)WARPS * (AMAF ? BoardWords<N>::value_amaf : BoardWords<N>::value) * sizeof(uint32_t);
+    cudaError_t e = cudaFuncSetAttribute(playout_warp_kernel<N, WARPS, BLOCKS_PER_SM, AMAF>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int64_t want = (a.local_units + WARPS - 1) / WARPS;
     const int64_t cap = (int64_t)sm_count * BLOCKS_PER_SM;
     const int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
     if (info) { info->grid = grid; info->block = WARPS * 32; info->smem = smem; info->name = "playout_warp_kernel"; }
-    playout_warp_kernel<N, WARPS, BLOCKS_PER_SM><<<grid, WARPS * 32, smem, s>>>(a);
+    playout_warp_kernel<N, WARPS, BLOCKS_PER_SM, AMAF><<<grid, WARPS * 32, smem, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -668,9 +714,9 @@ void build_jump(const RngParams& prm, int steps, JumpTable* out) {
 cudaError_t launch_playout_warp(int n, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
     // 8 warps per block, 4 blocks per SM: 32 resident playouts per SM, 64 registers per thread
     switch (n) {
-        case 9: return launch_w<9, 8, 4>(a, sm_count, s, info);
-        case 13: return launch_w<13, 8, 4>(a, sm_count, s, info);
-        case 19: return launch_w<19, 8, 4>(a, sm_count, s, info);
+        case 9: return a.amaf ? launch_w<9, 8, 4, true>(a, sm_count, s, info) : launch_w<9, 8, 4, false>(a, sm_count, s, info);
+        case 13: return a.amaf ? launch_w<13, 8, 4, true>(a, sm_count, s, info) : launch_w<13, 8, 4, false>(a, sm_count, s, info);
+        case 19: return a.amaf ? launch_w<19, 8, 4, true>(a, sm_count, s, info) : launch_w<19, 8, 4, false>(a, sm_count, s, info);
     }
     return cudaErrorInvalidValue;
 }

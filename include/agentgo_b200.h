@@ -186,6 +186,24 @@ void* agb_stream(agb_engine* h);
 typedef int (*agb_allreduce_fn)(void* ctx, void* dev_int64, int count, void* cuda_stream);
 int agb_set_allreduce(agb_engine* h, agb_allreduce_fn fn, void* ctx);
 
+/* AMAF first-play marks (AgentGo.cpp:289-290,304,319,329-338), candidate mode (C >= 1) only.
+ * Integer contract: amaf[which][sign][step][q], int64, AGB_AMAF_WORDS(N) elements, accumulated
+ * over ALL candidates like the reference's global amaf1/amaf2:
+ *   which 0: q's first play by `colour` (mark),  1: by the enemy (mark2), counted only when the
+ *            agent has no mark <= 40 at q (the `else if` of :334);
+ *   sign  0: sum of w over playouts with w >= 0,  1: sum of w over playouts with w < 0
+ *            (w = diff - avrg_win);
+ *   step  = cstep of that first play, 2..AGB_AMAF_RANGE (0 and 1 stay zero);  q = row*N + col.
+ * The reference's doubles follow on the host:
+ *   amaf1[q] =  sum_s 100*amaf[s-1]*index_c*(A[0][0][s][q] + cnsv*A[0][1][s][q])
+ *   amaf2[q] = -sum_s 100*amaf[s-1]*index_c*(A[1][0][s][q] + cnsv*A[1][1][s][q])          */
+#define AGB_AMAF_RANGE 40   /* GoContest/AgentGo.h:16 */
+#define AGB_AMAF_WORDS(n) (2 * 2 * (AGB_AMAF_RANGE + 1) * (n) * (n))
+int agb_playouts_amaf(agb_engine* h, int colour, const int16_t* cand_rc, int C, int64_t P,
+                      int avrg_win, uint64_t seed_base, uint32_t position_id,
+                      int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
+                      int64_t* amaf /* AGB_AMAF_WORDS(N) */, agb_stats* stats);
+
 /* batch of B independent positions (config 3): root-mode, P playouts each,
  * position b uses position_id = first_position_id + b and is evaluated by the
  * shard with (first_position_id + b) % shard_count == shard_rank.

@@ -570,6 +570,54 @@ int orc_playouts(void* vroot, int colour, int cand_row, int cand_col, uint32_t p
     return 0;
 }
 
+#define AMAF_RANGE 40            /* GoContest/AgentGo.h:16 */
+
+/* AMAF first-play marks, AgentGo.cpp:286-338 (candidate mode); contract: see ref_harness.cpp.
+ * amaf[which][sign][step 0..40][q], which 0 = agent / 1 = enemy first play, sign 0: w >= 0. */
+int orc_playouts_amaf(void* vroot, int colour, int cand_row, int cand_col, uint32_t position_id,
+                      uint32_t cand_idx, int64_t p_begin, int64_t p_end, int64_t p_stride,
+                      uint64_t seed_base, int avrg_win, int64_t* out3, int64_t* amaf) {
+    const OBoard* root = (const OBoard*)vroot;
+    int agent = colour, enemy = 3 - colour, nn = root->nn, n = root->n, S = AMAF_RANGE + 1, q;
+    int mark[MAXNN], mark2[MAXNN];
+    int64_t p;
+    OBoard *start, *bd;
+    ORng rng;
+    if (cand_row < 0) return -1;
+    start = (OBoard*)malloc(sizeof(OBoard));
+    bd = (OBoard*)malloc(sizeof(OBoard));
+    if (!start || !bd) { free(start); free(bd); return -4; }
+    *start = *root;
+    if (start->data[cand_row * n + cand_col] != AGB_EMPTY) { free(start); free(bd); return -2; }
+    o_put(start, agent, cand_row, cand_col);                      /* AgentGo.cpp:83 */
+    rng.draws = 0;
+    for (p = p_begin; p < p_end; p += p_stride) {
+        int agent_go = 1, enemy_go = 1, cstep = 1, r, w, sign;
+        o_seed(&rng, agb_playout_seed(seed_base, position_id, cand_idx, (uint64_t)p));
+        *bd = *start;                                             /* :288 */
+        memset(mark, 0, sizeof(mark));                            /* :289-290 */
+        memset(mark2, 0, sizeof(mark2));
+        while (agent_go || enemy_go) {                            /* :295-325 */
+            cstep++;
+            r = random_piece(bd, &rng, enemy);
+            if (r >= 0) { o_put(bd, enemy, r / n, r % n); enemy_go = 1; if (mark2[r] == 0) mark2[r] = cstep; }
+            else { enemy_go = 0; o_pass(bd, enemy); }
+            r = random_piece(bd, &rng, agent);
+            if (r >= 0) { o_put(bd, agent, r / n, r % n); agent_go = 1; if (mark[r] == 0) mark[r] = cstep; }
+            else { agent_go = 0; o_pass(bd, agent); }
+        }
+        w = count_score(bd, agent) - count_score(bd, enemy) - avrg_win;     /* :327 */
+        sign = w >= 0 ? 0 : 1;
+        if (out3) { if (w >= 0) { out3[0]++; out3[1] += w; } else out3[2] += w; }
+        for (q = 0; q < nn; q++) {                                /* :329-338 */
+            if (mark[q] != 0 && mark[q] <= AMAF_RANGE) amaf[((0 * 2 + sign) * S + mark[q]) * nn + q] += w;
+            else if (mark2[q] != 0 && mark2[q] <= AMAF_RANGE) amaf[((1 * 2 + sign) * S + mark2[q]) * nn + q] += w;
+        }
+    }
+    free(start); free(bd);
+    return 0;
+}
+
 /* CPU baseline thread pool: the reference's policy (2*cores+2 threads, TinyMT.h:543-546;
  * one job per candidate, AgentGo.cpp:595-600) with pthreads; jobs are (candidate, chunk). */
 typedef struct {

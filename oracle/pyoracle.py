@@ -22,6 +22,7 @@ PORT_LIB = os.path.join(HERE, "liboracle_port.so")
 CHECKS = {"suicide": 0, "kill": 1, "survive": 2, "dying": 3, "chase": 4,
           "true_eye": 5, "compete": 6, "no_sense": 7}
 ROOT_CANDIDATE = 0xFFFFFFFF
+AMAF_RANGE = 40          # GoContest/AgentGo.h:16
 
 
 def move(colour, row, col):
@@ -81,6 +82,8 @@ def _bind(lib):
     lib.orc_playouts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
                                  C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int,
                                  i16p, i64p, i64p]
+    lib.orc_playouts_amaf.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                      C.c_int64, C.c_int64, C.c_int64, C.c_uint64, C.c_int, i64p, i64p]
     lib.orc_playouts_mt.argtypes = [C.c_void_p, C.c_int, i16p, C.c_int, C.c_int64, C.c_uint32,
                                     C.c_uint64, C.c_int, C.c_int, i16p, i64p, i64p]
     return lib
@@ -160,6 +163,21 @@ class OracleBoard:
         self.lib.orc_random_game(self.h, first_colour, n_moves, seed,
                                  out.ctypes.data_as(C.POINTER(C.c_uint32)))
         return out
+
+    def playouts_amaf(self, colour, cands, P, avrg_win=0, seed_base=20151001, position_id=0):
+        """Candidate-mode playouts with AMAF first-play marks (AgentGo.cpp:286-338).
+        returns (wins, sum_pos, sum_neg, amaf) with amaf int64 [2 which][2 sign][41 step][NN],
+        accumulated over all candidates like the reference's global amaf1/amaf2."""
+        nn = self.n * self.n
+        out3 = np.zeros((len(cands), 3), dtype=np.int64)
+        amaf = np.zeros((2, 2, AMAF_RANGE + 1, nn), dtype=np.int64)
+        for c, (row, col) in enumerate(cands):
+            r = self.lib.orc_playouts_amaf(self.h, colour, row, col, position_id, c, 0, P, 1, seed_base, avrg_win,
+                                           out3[c].ctypes.data_as(C.POINTER(C.c_int64)),
+                                           amaf.ctypes.data_as(C.POINTER(C.c_int64)))
+            if r:
+                raise RuntimeError("orc_playouts_amaf -> %d" % r)
+        return out3[:, 0].copy(), out3[:, 1].copy(), out3[:, 2].copy(), amaf
 
     def playouts(self, colour, cands, P, avrg_win=0, seed_base=20151001, position_id=0,
                  want_diffs=True, threads=1, with_stats=False):

@@ -204,6 +204,60 @@ int orc_playouts(void* vroot, int colour, int cand_row, int cand_col, uint32_t p
     return 0;
 }
 
+/* AMAF first-play marks, restating AgentGo.cpp:286-338 (candidate mode only): per playout
+ * mark[q] / mark2[q] = cstep of the first agent / enemy play at q (cstep starts at 1 and is
+ * incremented at the top of every pair, so the first pair has cstep 2); after the playout, with
+ * w = diff - avrg_win, point q contributes w to the agent table when 0 < mark[q] <= AMAF_RANGE,
+ * else to the enemy table when 0 < mark2[q] <= AMAF_RANGE (the `else if` of :334).
+ * Integer contract: amaf[which][sign][step][q] (int64, which 0 = agent / 1 = enemy first play,
+ * sign 0 = sum of w >= 0 / 1 = sum of w < 0, step 0..AMAF_RANGE, q = row*N+col), accumulated
+ * over all playouts; the reference's doubles are
+ *   amaf1[q] =  sum_s 100*amaf[s-1]*index_c*(A[0][0][s][q] + cnsv*A[0][1][s][q])   (:332)
+ *   amaf2[q] = -sum_s 100*amaf[s-1]*index_c*(A[1][0][s][q] + cnsv*A[1][1][s][q])   (:335)  */
+int orc_playouts_amaf(void* vroot, int colour, int cand_row, int cand_col, uint32_t position_id,
+                      uint32_t cand_idx, int64_t p_begin, int64_t p_end, int64_t p_stride,
+                      uint64_t seed_base, int avrg_win, int64_t* out3, int64_t* amaf) {
+    Board* root = (Board*)vroot;
+    const int agent = colour, enemy = 3 - colour;
+    if (cand_row < 0) return -1;
+    Board start(*root);
+    if (start.data[cand_row][cand_col] != GO_NULL) return -2;
+    start.put(agent, cand_row, cand_col);                      /* AgentGo.cpp:83 */
+    Board* bd = new Board();
+    static thread_local int mark[NN], mark2[NN];
+    const int S = AMAF_RANGE + 1;
+    for (int64_t p = p_begin; p < p_end; p += p_stride) {
+        rng_seed(agb_playout_seed(seed_base, position_id, cand_idx, (uint64_t)p));
+        bd->clone(start);
+        memset(mark, 0, sizeof(mark));
+        memset(mark2, 0, sizeof(mark2));
+        bool agent_go = 1, enemy_go = 1;
+        int cstep = 1;
+        while (agent_go || enemy_go) {
+            cstep++;
+            Piece r = bd->getRandomPiece(enemy);
+            if (!r.isEmpty()) {
+                bd->put(r); enemy_go = true;
+                if (mark2[r.row * BOARD_SIZE + r.col] == 0) mark2[r.row * BOARD_SIZE + r.col] = cstep;
+            } else { enemy_go = false; bd->pass(enemy); }
+            r = bd->getRandomPiece(agent);
+            if (!r.isEmpty()) {
+                bd->put(r); agent_go = true;
+                if (mark[r.row * BOARD_SIZE + r.col] == 0) mark[r.row * BOARD_SIZE + r.col] = cstep;
+            } else { agent_go = false; bd->pass(agent); }
+        }
+        const int w = bd->countScore(agent) - bd->countScore(enemy) - avrg_win;
+        const int sign = w >= 0 ? 0 : 1;
+        if (out3) { if (w >= 0) { out3[0]++; out3[1] += w; } else out3[2] += w; }
+        for (int q = 0; q < NN; q++) {
+            if (mark[q] != 0 && mark[q] <= AMAF_RANGE) amaf[((0 * 2 + sign) * S + mark[q]) * NN + q] += w;
+            else if (mark2[q] != 0 && mark2[q] <= AMAF_RANGE) amaf[((1 * 2 + sign) * S + mark2[q]) * NN + q] += w;
+        }
+    }
+    delete bd;
+    return 0;
+}
+
 /* CPU baseline: the reference's thread policy (2*cores+2 threads, TinyMT.h:543-546;
  * one job per candidate, AgentGo.cpp:595-600) re-created with std::thread.  Jobs are
  * (candidate, chunk) pairs pulled from an atomic counter so root mode also scales.

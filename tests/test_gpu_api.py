@@ -180,3 +180,24 @@ def test_full_size_config2_bit_exact(built_lib):
     assert (d == od).all()
     assert (w[0], sp[0], sn[0]) == (ow[0], osp[0], osn[0])
     assert st["moves"] == ost["moves"] and st["rng_draws"] == ost["rng_draws"]
+
+
+def test_amaf_marks_match_oracle(built_lib):
+    """'next' row 1: AMAF first-play marks, integer contract of agb_playouts_amaf."""
+    for n, P in ((9, 200), (13, 120), (19, 80)):
+        mv = po.OracleBoard(n, "best").random_game(1, n * n // 3, 321)
+        ob = po.OracleBoard(n, "best").replay(mv)
+        st = ob.export_state()
+        emp = [i for i in range(n * n) if st[16 + i] == 0][::5][:9]
+        cands = [(i // n, i % n) for i in emp]
+        ow, osp, osn, oa = ob.playouts_amaf(2, cands, P, avrg_win=1, seed_base=5, position_id=2)
+        e = ag.Engine(n).replay(mv)
+        w, sp, sn, a, stt = e.playouts_amaf(2, cands, P, avrg_win=1, seed_base=5, position_id=2)
+        assert (w == ow).all() and (sp == osp).all() and (sn == osn).all()
+        assert (a == oa).all(), np.argwhere(a != oa)[:5]
+        assert a[:, :, :2, :].sum() == 0 and np.count_nonzero(a) > 100
+        # same counters as the plain evaluation
+        w2, sp2, sn2, _, _ = e.playouts(2, cands, P, avrg_win=1, seed_base=5, position_id=2)
+        assert (w2 == w).all() and (sp2 == sp).all() and (sn2 == sn).all()
+    with pytest.raises(ag.AgbError):
+        ag.Engine(9, kernel=ag.KERNEL_THREAD).playouts_amaf(1, [(1, 1)], 10)

@@ -136,3 +136,25 @@ def test_thread_count_does_not_change_results(port_lib):
     a7 = b.playouts(1, [(2, 2), (4, 4)], 300, avrg_win=1, threads=7)
     for x, y in zip(a1, a7):
         assert (x == y).all()
+
+
+def test_amaf_marks_port_equals_reference(port_lib):
+    """AMAF first-play marks (AgentGo.cpp:286-338): the C restatement against the compiled reference."""
+    for n in (9, 13):
+        if "reference" not in kinds(n):
+            pytest.skip("oracle/_ref not built")
+        mv = po.OracleBoard(n, "reference").random_game(1, n * n // 3, 321)
+        r = po.OracleBoard(n, "reference").replay(mv)
+        p = po.OracleBoard(n, "port").replay(mv)
+        st = r.export_state()
+        emp = [i for i in range(n * n) if st[16 + i] == 0][::7][:5]
+        cands = [(i // n, i % n) for i in emp]
+        A = r.playouts_amaf(2, cands, 50, avrg_win=1, seed_base=5)
+        B = p.playouts_amaf(2, cands, 50, avrg_win=1, seed_base=5)
+        for x, y in zip(A, B):
+            assert (x == y).all()
+        plain = r.playouts(2, cands, 50, avrg_win=1, seed_base=5, threads=1)
+        for i in range(3):
+            assert (A[i] == plain[i]).all()
+        # every playout contributes w to at most one table per point, steps 2..40 only
+        assert A[3][:, :, :2, :].sum() == 0
