@@ -45,7 +45,7 @@ class Config(C.Structure):
     _fields_ = [("board_size", C.c_int), ("device", C.c_int), ("kernel", C.c_int),
                 ("shard_rank", C.c_int), ("shard_count", C.c_int),
                 ("mat1", C.c_uint32), ("mat2", C.c_uint32), ("tmat", C.c_uint32),
-                ("max_moves", C.c_int)]
+                ("max_moves", C.c_int), ("genmove_amaf", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -172,12 +172,13 @@ class Engine:
     """
 
     def __init__(self, board_size=13, device=0, kernel=KERNEL_AUTO, shard_rank=0, shard_count=1,
-                 max_moves=0):
+                 max_moves=0, genmove_amaf=0):
         self._l = lib()
         cfg = Config()
         self._l.agb_default_config(C.byref(cfg))
         cfg.board_size, cfg.device, cfg.kernel = board_size, device, kernel
         cfg.shard_rank, cfg.shard_count, cfg.max_moves = shard_rank, shard_count, max_moves
+        cfg.genmove_amaf = genmove_amaf
         h = C.c_void_p()
         st = self._l.agb_create(C.byref(cfg), C.byref(h))
         if st:

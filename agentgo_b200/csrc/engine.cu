@@ -345,12 +345,40 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
     if (C > 0) {
         std::vector<int64_t> cw(C), csp(C), csn(C);
         if (P_cand < 0) P_cand = (-P_cand + C - 1) / C;      // fixed budget per genmove, split over candidates
-        st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false);
+        const bool use_amaf = cfg.genmove_amaf != 0 && cfg.kernel != AGB_KERNEL_THREAD;
+        std::vector<int64_t> amaf;
+        if (use_amaf) amaf.resize((size_t)AGB_AMAF_WORDS(n));
+        st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false, use_amaf);
         if (st) return st;
-        if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1))) return st;
+        if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1, use_amaf ? amaf.data() : nullptr))) return st;
         acc.device_ms += st1.device_ms; acc.playouts += st1.playouts; acc.moves += st1.moves;
         acc.rng_draws += st1.rng_draws; acc.kernel_launches += st1.kernel_launches;
         const double cnsv = std::pow(2.0, avrg_win * 0.01);  // index_cnsv = 0.01, AgentGo.cpp:25,99
+        // AMAF terms (:86-94,:329-338): decay table over the step of the first play, from the number
+        // of stones after the candidate is played; index_amaf_* defaults of :21-24, index_c = 1.
+        std::vector<double> amaf12((size_t)n * n, 0.0);
+        if (use_amaf) {
+            const int NN = n * n, S = AGB_AMAF_RANGE + 1;
+            const int num_piece = board.position().num_black + board.position().num_white + 1;
+            const double num_a = 1.0 / (40.0 - (39.0 / 180) * num_piece);
+            const double num_b = 0.3 - (0.3 / 180) * num_piece;
+            double tab[AGB_AMAF_RANGE];
+            for (int k = 0; k < AGB_AMAF_RANGE; k++) {
+                double v = 1 - std::pow(num_a * k, num_b);
+                if (!(v >= 0)) v = 0;               // also catches NaN (negative base on boards > 13x13)
+                else if (v > 1) v = 1;
+                tab[k] = v;
+            }
+            for (int q = 0; q < NN; q++) {
+                double a1 = 0, a2 = 0;
+                for (int sidx = 2; sidx <= AGB_AMAF_RANGE; sidx++) {
+                    const double t = 100.0 * tab[sidx - 1];
+                    a1 += t * ((double)amaf[((size_t)(0 * 2 + 0) * S + sidx) * NN + q] + cnsv * (double)amaf[((size_t)(0 * 2 + 1) * S + sidx) * NN + q]);
+                    a2 -= t * ((double)amaf[((size_t)(1 * 2 + 0) * S + sidx) * NN + q] + cnsv * (double)amaf[((size_t)(1 * 2 + 1) * S + sidx) * NN + q]);
+                }
+                amaf12[q] = a1 + a2;
+            }
+        }
         // argmax over every eligible point in row-major order, first maximum wins (:647-676).
         // Points the candidate filter dropped only for checkNoSense still compete with mark 0.
         bool init = false;
@@ -365,6 +393,7 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
                     mark = 2.0 * 100.0 * ((double)csp[c] + cnsv * (double)csn[c]);
                     c++;
                 }
+                mark += amaf12[(size_t)i * n + j];                                      // :654-655
                 if (!board.is_eligible(colour, i, j)) continue;
                 if (!init || mark > best) { best = mark; *row = i; *col = j; init = true; }
             }

@@ -2,11 +2,13 @@
 // self-play driver for BASELINE.json configs[3] (device-timed genmove latency).
 //
 //   agentgo_gtp [--boardsize N] [--playouts P] [--total-playouts M] [--root-playouts R]
-//               [--device D] [--seed S] [--kernel auto|thread|warp] [--selfplay [--max-moves K]]
+//               [--device D] [--seed S] [--kernel auto|thread|warp] [--amaf]
+//               [--selfplay [--max-moves K]]
 //
 //   --playouts P        playouts per candidate (reference: numset = 150, AgentGo.cpp:85)
 //   --total-playouts M  fixed budget per genmove, split evenly over the candidates
 //   --root-playouts R   testAvrgWin playouts (reference: 500, AgentGo.cpp:413)
+//   --amaf              add the AMAF terms amaf1 + amaf2 (AgentGo.cpp:329-338,654-655) to the marks
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -40,6 +42,7 @@ int main(int argc, char** argv) {
         else if (a == "--seed") seed = strtoull(next("--seed"), nullptr, 10);
         else if (a == "--max-moves") max_moves = atoi(next("--max-moves"));
         else if (a == "--selfplay") selfplay = true;
+        else if (a == "--amaf") cfg.genmove_amaf = 1;
         else if (a == "--kernel") {
             const std::string k = next("--kernel");
             cfg.kernel = k == "thread" ? AGB_KERNEL_THREAD : (k == "warp" ? AGB_KERNEL_WARP : AGB_KERNEL_AUTO);

@@ -92,6 +92,8 @@ typedef struct agb_config {
     int shard_count;     /*   g % shard_count == shard_rank   (1 => everything)     */
     uint32_t mat1, mat2, tmat; /* TinyMT32 parameters; 0,0,0 => RFC 8682 set      */
     int max_moves;       /* per-playout move cap, 0 => default (fault detector)    */
+    int genmove_amaf;    /* agb_genmove: 0 flat MC only (default); 1 adds the AMAF terms
+                            amaf1 + amaf2 of AgentGo.cpp:329-338,654-655                 */
 } agb_config;
 
 typedef struct agb_engine agb_engine;
@@ -216,7 +218,8 @@ int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
 /* GTP-compat genmove (AgentGo.cpp:573-688 without the static heuristics and
  * AMAF terms, which are outside the flat-MC path): root playouts -> avrg_win,
  * candidate filter, P playouts per candidate, argmax of
- * sum_pos + cnsv*sum_neg.  *is_pass = 1 when no candidate exists.  The move
+ * sum_pos + cnsv*sum_neg (plus amaf1 + amaf2 when cfg.genmove_amaf).  *is_pass = 1
+ * when no candidate exists.  The move
  * is NOT played on the engine's board (the caller does, GTPAdapter.cpp:78).
  * P_per_candidate < 0: |P_per_candidate| is a fixed playout budget per genmove,
  * split evenly (rounded up) over the candidates.                              */

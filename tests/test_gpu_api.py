@@ -124,7 +124,7 @@ def test_edge_cases(built_lib):
     assert (e2.export_state() == ob.export_state()).all()
 
 
-def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base):
+def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base, use_amaf=False):
     w, sp, sn, _ = ob.playouts(colour, None, P_root, seed_base=seed_base, want_diffs=False, threads=0)
     tot = int(sp[0] + sn[0])
     avrg = abs(tot) // P_root * (1 if tot >= 0 else -1)          # C truncation, AgentGo.cpp:447
@@ -137,9 +137,22 @@ def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base):
                 continue
             cands.append((i, j))
     marks = {}
+    amaf12 = np.zeros(n * n)
     if cands:
-        w, sp, sn, _ = ob.playouts(colour, cands, P_cand, avrg_win=avrg, seed_base=seed_base + 1, want_diffs=False, threads=0)
         cnsv = 2.0 ** (avrg * 0.01)
+        if use_amaf:
+            w, sp, sn, A = ob.playouts_amaf(colour, cands, P_cand, avrg_win=avrg, seed_base=seed_base + 1)
+            num_piece = int(st[1] + st[2]) + 1
+            num_a = 1.0 / (40.0 - (39.0 / 180) * num_piece)
+            num_b = 0.3 - (0.3 / 180) * num_piece
+            for s in range(2, 41):
+                k = s - 1
+                base = num_a * k
+                v = 1 - (base ** num_b if base >= 0 else float("nan"))
+                v = 0.0 if not (v >= 0) else min(v, 1.0)
+                amaf12 += 100.0 * v * ((A[0, 0, s] + cnsv * A[0, 1, s]) - (A[1, 0, s] + cnsv * A[1, 1, s]))
+        else:
+            w, sp, sn, _ = ob.playouts(colour, cands, P_cand, avrg_win=avrg, seed_base=seed_base + 1, want_diffs=False, threads=0)
         for c, a, b in zip(cands, sp, sn):
             marks[c] = 2.0 * 100.0 * (float(a) + cnsv * float(b))
     best, arg = None, None
@@ -147,7 +160,7 @@ def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base):
         for j in range(n):
             if st[16 + i * n + j] == 0 and not ob.check("true_eye", colour, i, j) and \
                     not ob.check("suicide", colour, i, j) and not ob.check("compete", colour, i, j):
-                m = marks.get((i, j), 0.0)
+                m = marks.get((i, j), 0.0) + amaf12[i * n + j]
                 if best is None or m > best:
                     best, arg = m, (i, j)
     return arg if cands else None
@@ -162,6 +175,10 @@ def test_genmove_matches_oracle_restatement(built_lib):
         got, st = e.genmove(colour, 60, 200, seed_base=777)
         assert got == _oracle_genmove(ob, n, colour, 60, 200, 777)
         assert st["playouts"] > 200
+        # with the AMAF terms of AgentGo.cpp:329-338,654-655
+        e2 = ag.Engine(n, genmove_amaf=1).replay(mv)
+        got2, _ = e2.genmove(colour, 60, 200, seed_base=777)
+        assert got2 == _oracle_genmove(ob, n, colour, 60, 200, 777, use_amaf=True)
 
 
 def test_full_size_config2_bit_exact(built_lib):
