@@ -31,7 +31,7 @@ SYMBOLS = [
     "agb_get_board", "agb_check", "agb_count_score", "agb_export_state", "agb_playouts",
     "agb_playouts_amaf", "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
     "agb_set_allreduce", "agb_playouts_batch", "agb_genmove", "agb_measure_peaks",
-    "agb_debug_violations",
+    "agb_debug_violations", "agb_attach_nccl", "agb_detach_nccl",
 ]
 
 

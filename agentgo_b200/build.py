@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(HERE, "..", "include")
 LIB = os.path.join(HERE, "libagentgo_b200.so")
 GTP = os.path.join(HERE, "agentgo_gtp")
-SOURCES = ["host_board.cpp", "engine.cu", "playout_thread.cu", "playout_warp.cu", "diag.cu", "capi.cpp"]
+SOURCES = ["host_board.cpp", "engine.cu", "playout_thread.cu", "playout_warp.cu", "diag.cu", "capi.cpp", "nccl_group.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", INCLUDE]
@@ -59,7 +59,7 @@ def build(force=False, verbose=False, debug=False):
                 sys.stderr.write(out)
         if failed:
             raise RuntimeError("CUDA build failed")
-        cmd = [NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     if debug:
         return lib
@@ -67,7 +67,7 @@ def build(force=False, verbose=False, debug=False):
     if os.path.exists(gtp_src) and (force or _stale(GTP, deps + [LIB])):
         cmd = ["g++", "-O2", "-std=c++17", "-I", CSRC, "-I", INCLUDE, gtp_src,
                os.path.join(CSRC, "gtp_adapter.cpp"), "-o", GTP,
-               "-L", HERE, "-lagentgo_b200", "-Wl,-rpath,$ORIGIN", "-ldl"]
+               "-L", HERE, "-lagentgo_b200", "-Wl,-rpath,$ORIGIN", "-ldl", "-pthread"]
         subprocess.check_call(cmd)
     return LIB
 

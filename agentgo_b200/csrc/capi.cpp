@@ -11,10 +11,6 @@
 
 using agb::Engine;
 
-struct agb_engine {
-    Engine* e;
-};
-
 static thread_local std::string g_create_error;
 
 #define AGB_GUARD_BEGIN try {

@@ -81,4 +81,9 @@ private:
 
 }  // namespace agb
 
+// the opaque handle of the C ABI
+struct agb_engine {
+    agb::Engine* e;
+};
+
 #endif

@@ -17,6 +17,7 @@
 
 #include <chrono>
 #include <iostream>
+#include <thread>
 
 #define STR_VERSION "0.0.1"
 #define STR_NAME "AgentGo"
@@ -120,7 +121,23 @@ bool GTPAdapter::HandleLine(const std::string& line, std::ostream& out) {
 // acknowledged and ignored because BOARD_SIZE is a compile-time 13.  Here a supported size
 // (9, 13, 19) is honoured; anything else is acknowledged and ignored like the reference does.
 void MyGame::onBoardSize(int sz) {
-    if (agb_boardsize(eng, sz) == AGB_OK) step = 0;
+    if (agb_boardsize(eng, sz) == AGB_OK) {
+        step = 0;
+        for (agb_engine* p : peers) agb_boardsize(p, sz);
+    }
+}
+
+void MyGame::onClear() {
+    step = 0;
+    for (agb_engine* p : peers) agb_clear_board(p);
+}
+
+void MyGame::onPlay(int isW, int a, int b) {
+    for (agb_engine* p : peers) agb_play(p, isW + 1, a, b);
+}
+
+void MyGame::onMoved(int isW, int a, int b) {
+    for (agb_engine* p : peers) agb_play(p, isW + 1, a, b);
 }
 
 // MyGame::onMove (AgentGo.cpp:449-693) without the 13x13 opening book of steps 1-4 (:468-572),
@@ -129,8 +146,17 @@ void MyGame::onBoardSize(int sz) {
 bool MyGame::onMove(int isW, int& a, int& b) {
     step += 1;
     int row = -1, col = -1, is_pass = 1;
-    const int st = agb_genmove(eng, isW + 1, P_cand, P_root, seed + 2ull * (unsigned long long)step, &row, &col,
-                               &is_pass, &last);
+    const unsigned long long sd = seed + 2ull * (unsigned long long)step;
+    // every engine of a multi-GPU group evaluates its shard of the same genmove; the NCCL hook
+    // inside sums the counters, so all of them return the same move
+    std::vector<std::thread> th;
+    for (agb_engine* p : peers)
+        th.emplace_back([=]() {
+            int r = -1, c = -1, ps = 1;
+            agb_genmove(p, isW + 1, P_cand, P_root, sd, &r, &c, &ps, nullptr);
+        });
+    const int st = agb_genmove(eng, isW + 1, P_cand, P_root, sd, &row, &col, &is_pass, &last);
+    for (std::thread& t : th) t.join();
     if (st != AGB_OK) {
         fprintf(stderr, "agb_genmove failed: %s\n", agb_last_error(eng));
         return false;

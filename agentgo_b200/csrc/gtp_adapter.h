@@ -10,6 +10,7 @@
 
 #include <iosfwd>
 #include <string>
+#include <vector>
 
 #include "agentgo_b200.h"
 
@@ -49,16 +50,19 @@ public:
         last.device_ms = 0; last.playouts = 0;
     }
     agb_stats last;       // statistics of the last genmove
+    // further engines of a multi-GPU group (agb_attach_nccl): they mirror every board change and
+    // run the same genmove concurrently, one host thread each
+    std::vector<agb_engine*> peers;
 
 private:
     int step;
     long long P_cand, P_root;
     unsigned long long seed;
-    void onClear() override { step = 0; }
+    void onClear() override;
     void onBoardSize(int sz) override;
-    void onPlay(int, int, int) override {}
+    void onPlay(int isW, int a, int b) override;
     bool onMove(int isW, int& a, int& b) override;
-    void onMoved(int, int, int) override {}
+    void onMoved(int isW, int a, int b) override;
 };
 
 #endif

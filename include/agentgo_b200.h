@@ -188,6 +188,14 @@ void* agb_stream(agb_engine* h);
 typedef int (*agb_allreduce_fn)(void* ctx, void* dev_int64, int count, void* cuda_stream);
 int agb_set_allreduce(agb_engine* h, agb_allreduce_fn fn, void* ctx);
 
+/* Single-process multi-GPU: engines[i] must be shard i of n on its own device.  Builds one NCCL
+ * communicator (ncclCommInitAll; libnccl is dlopen'ed at this point) and installs the allreduce
+ * hook on every engine.  Afterwards issue the SAME agb_playouts* / agb_genmove call on every engine
+ * concurrently, one host thread per engine: each returns the counters summed over all GPUs.     */
+typedef struct agb_nccl_group agb_nccl_group;
+int agb_attach_nccl(agb_engine** engines, int n, agb_nccl_group** out);
+void agb_detach_nccl(agb_nccl_group* g);
+
 /* AMAF first-play marks (AgentGo.cpp:289-290,304,319,329-338), candidate mode (C >= 1) only.
  * Integer contract: amaf[which][sign][step][q], int64, AGB_AMAF_WORDS(N) elements, accumulated
  * over ALL candidates like the reference's global amaf1/amaf2:

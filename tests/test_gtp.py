@@ -56,3 +56,18 @@ def test_genmove_and_selfplay_on_gpu(built_lib):
     import json
     sp = json.loads(r.stdout.strip().splitlines()[-1])["selfplay"]
     assert sp["genmoves"] >= 20 and sp["device_ms_median"] > 0
+
+
+@pytest.mark.gpu
+def test_multi_gpu_selfplay_equals_single_gpu(built_lib):
+    """agentgo_gtp --gpus 2 (one process, two engines, NCCL allreduce through agb_attach_nccl) must
+    play exactly the game of --gpus 1: results do not depend on how playouts are partitioned."""
+    if ag.lib().agb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    games = []
+    for gpus in ("1", "2"):
+        r = subprocess.run([GTP, "--boardsize", "9", "--selfplay", "--playouts", "48", "--root-playouts", "96",
+                            "--max-moves", "60", "--gpus", gpus, "--amaf"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        games.append([l for l in r.stderr.splitlines() if l[:3].strip().isdigit()])
+    assert len(games[0]) == 60 and games[0] == games[1]
