@@ -97,6 +97,7 @@ struct WarpBoard {
     int ko_key;          // exist_compete ? compete colour<<16 | idx : -1
     int last0, last1;    // last_move[colour-1] as idx, -1 = none
     int ending;          // game_ending
+    int n_e;             // >= 0: scratch[0..n_e) lists the empty points (kept while complex mode lasts); -1: stale
     // --- random numbers: a ring of pre-generated rand() values (see refill) ---
     SmemArr<uint16_t> ring;      // kRing entries, entry (p & (kRing-1)) holds draw number p of this playout
     uint32_t g0, g1, g2, g3;     // generator state at draw number gen_end (warp-uniform)
@@ -242,16 +243,21 @@ struct WarpBoard {
     __device__ __forceinline__ int random_piece_complex(int agent) {
         const int spaces = NN - stones;
         if (spaces == 0) return -1;
-        int n_e = 0;
+        if (n_e < 0) {
+            // compact the empty points with ballots (any order).  Complex mode is sticky
+            // (game_ending, :348-351), so the list is then maintained by put / kill_string
+            // instead of being rebuilt from all (N+2)^2 cells on each of the ~50 following calls.
+            n_e = 0;
 #pragma unroll 1
-        for (int base = 0; base < NP; base += 32) {
-            const int idx = base + lane;
-            const bool e = idx < NP && fCol(w0[idx]) == 0;
-            const unsigned m = __ballot_sync(kFull, e);
-            if (e) scratch[n_e + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
-            n_e += __popc(m);
+            for (int base = 0; base < NP; base += 32) {
+                const int idx = base + lane;
+                const bool e = idx < NP && fCol(w0[idx]) == 0;
+                const unsigned m = __ballot_sync(kFull, e);
+                if (e) scratch[n_e + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
+                n_e += __popc(m);
+            }
+            __syncwarp();
         }
-        __syncwarp();
         int reserved_total = 0;
 #pragma unroll 1
         for (int base = 0; base < n_e; base += 8) {
@@ -298,6 +304,7 @@ struct WarpBoard {
             else complex_mode = true;
         }
         if (!complex_mode) {
+            n_e = -1;                                               // scratch is reused below
             const int lm = agent == 1 ? last1 : last0;              // opponent's last move
             if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
                 const Eval f = eval_cells<kEvalAll>(agent, lm + off_cell);
@@ -376,6 +383,7 @@ struct WarpBoard {
                 w0[k] = pack0(k, k, 0);
             }
             head = k;
+            if (n_e >= 0) { scratch[n_e] = (uint16_t)k; n_e++; }    // keep the list of empties current
 #pragma unroll
             for (int d = 0; d < 4; d++) {                           // one liberty back, :323-326
                 const uint32_t v = w0[k + (d == 0 ? -W : (d == 1 ? -1 : (d == 2 ? W : 1)))];
@@ -400,6 +408,19 @@ struct WarpBoard {
                 w0[sp] = (w0[sp] & ~(1023u << 10)) | ((uint32_t)sx << 10);
                 w0[sx] = (w0[sx] & ~1023u) | (uint32_t)sp;
             }
+        }
+        if (n_e >= 0) {                                             // keep the list of empties current
+#pragma unroll 1
+            for (int base = 0; base < n_e; base += 32) {
+                const int k = base + lane;
+                const unsigned m = __ballot_sync(kFull, k < n_e && scratch[k] == idx);
+                if (m) {
+                    scratch[base + __ffs(m) - 1] = scratch[n_e - 1];
+                    n_e--;
+                    break;
+                }
+            }
+            __syncwarp();
         }
         w0[idx] = pack0(idx, kNil, agent);                          // SetNode::init, SetNode.cpp:31-44
         w1[idx] = (uint32_t)idx << 16;
@@ -533,6 +554,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         bd.ending = pos.ending;
         bd.pos = 0;
         bd.gen_end = 0;
+        bd.n_e = -1;
         __syncwarp();
         {
             // tinymt32_init (RFC 8682)
