@@ -92,7 +92,7 @@ struct WarpBoard {
     int off_nb;          // offset of this lane's orthogonal neighbour (dir = lane & 3: up, left, down, right)
     int off_dg;          // offset of this lane's diagonal
     int off_cell;        // offset of this lane's cell in the 3x3 block around a point (cell = lane >> 2)
-    int head;            // first empty point, -1 = none
+    int head;            // first empty point, 0 (the sentinel cell) = none
     int stones;          // num_black + num_white (only the sum is ever read on this path)
     int ko_key;          // exist_compete ? compete colour<<16 | idx : -1
     int last0, last1;    // last_move[colour-1] as idx, -1 = none
@@ -376,12 +376,8 @@ struct WarpBoard {
             const int nx = fB(w);
             const int agent = fCol(w);
             stones--;
-            if (head >= 0) {                                        // push at the list head, :311-321
-                w0[k] = pack0(k, head, 0);
-                w0[head] = (w0[head] & ~1023u) | (uint32_t)k;
-            } else {
-                w0[k] = pack0(k, k, 0);
-            }
+            w0[k] = pack0(0, head, 0);                              // push at the list head, :311-321
+            w0[head] = (w0[head] & ~1023u) | (uint32_t)k;           // (head == 0: the sentinel)
             head = k;
             if (n_e >= 0) { scratch[n_e] = (uint16_t)k; n_e++; }    // keep the list of empties current
 #pragma unroll
@@ -398,16 +394,15 @@ struct WarpBoard {
     __device__ __forceinline__ void put(int agent, int idx) {
         stones++;
         ko_key = -1;
-        {                                                           // unlink from the empty list, :105-118
+        {
+            // unlink from the empty list (:105-118).  On the device the list uses cell 0 (a border
+            // cell) as sentinel instead of the reference's self-links: prev(first) = next(last) = 0,
+            // so removal and head insertion need no case distinction.
             const uint32_t w = w0[idx];
             const int sp = fA(w), sx = fB(w);
-            if (stones == NN) head = -1;
-            else if (sp == idx) { w0[sx] = (w0[sx] & ~1023u) | (uint32_t)sx; head = sx; }
-            else if (sx == idx) { w0[sp] = (w0[sp] & ~(1023u << 10)) | ((uint32_t)sp << 10); }
-            else {
-                w0[sp] = (w0[sp] & ~(1023u << 10)) | ((uint32_t)sx << 10);
-                w0[sx] = (w0[sx] & ~1023u) | (uint32_t)sp;
-            }
+            w0[sp] = (w0[sp] & ~(1023u << 10)) | ((uint32_t)sx << 10);
+            w0[sx] = (w0[sx] & ~1023u) | (uint32_t)sp;
+            if (sp == 0) head = sx;
         }
         if (n_e >= 0) {                                             // keep the list of empties current
 #pragma unroll 1
@@ -465,16 +460,31 @@ struct WarpBoard {
                 if (own_l) w0[tail_l] = (w0[tail_l] & ~(1023u << 10)) | ((uint32_t)target << 10);
                 w0[idx] = pack0(fk, kNil, agent);
                 w1[fk] = (uint32_t)hp_total | ((uint32_t)idx << 16);
-                // strings F_1..F_(k-1) are relabelled to Fk, each by its own lane (:284-289)
-                bool walk = own_l && root_l != fk;
-                int sidx = root_l;
+                // strings F_1..F_(k-1) are relabelled to Fk (:284-289)
+                const unsigned others = fr_mask & (fr_mask - 1u) ? fr_mask & ~(1u << (31 - __clz(fr_mask))) : 0u;
+                if (others && !(others & (others - 1u))) {
+                    // the usual case of a merge: one string, walked warp-uniformly
+                    const int d1 = __ffs(others) - 1;
+                    const int t1 = (int)(__shfl_sync(kFull, h_l, d1) >> 16);
 #pragma unroll 1
-                while (__ballot_sync(kFull, walk)) {
-                    if (walk) {
+                    for (int sidx = __shfl_sync(kFull, root_l, d1);;) {
                         const uint32_t w = w0[sidx];
                         w0[sidx] = (w & ~1023u) | (uint32_t)fk;
-                        walk = sidx != tail_l;
+                        if (sidx == t1) break;
                         sidx = fB(w);
+                    }
+                } else if (others) {
+                    // two or three strings: each is walked by its own lane
+                    bool walk = own_l && root_l != fk;
+                    int sidx = root_l;
+#pragma unroll 1
+                    while (__ballot_sync(kFull, walk)) {
+                        if (walk) {
+                            const uint32_t w = w0[sidx];
+                            w0[sidx] = (w & ~1023u) | (uint32_t)fk;
+                            walk = sidx != tail_l;
+                            sidx = fB(w);
+                        }
                     }
                 }
             }
@@ -751,12 +761,16 @@ void to_padded(const Position& p, PaddedPosition* out) {
         const uint32_t v0 = p.w0[idx], v1 = p.w1[idx];
         const int col = (int)((v0 >> 20) & 3u);
         const int a = (int)(v0 & 1023u), b = (int)((v0 >> 10) & 1023u);
-        const int pa = pad(a), pb = (col != 0 && b == kNil) ? kNil : pad(b);
+        int pa = pad(a), pb = (col != 0 && b == kNil) ? kNil : pad(b);
+        if (col == 0) {                 // empty list: self-links of the reference become the sentinel 0
+            if (a == idx) pa = 0;
+            if (b == idx) pb = 0;
+        }
         out->w0[pad(idx)] = (uint32_t)pa | ((uint32_t)pb << 10) | ((uint32_t)col << 20);
         const bool is_root = col != 0 && a == idx;                  // hp/tail are meaningful at roots only
         out->w1[pad(idx)] = is_root ? ((v1 & 0xffffu) | ((uint32_t)pad((int)(v1 >> 16)) << 16)) : 0u;
     }
-    out->head = (int16_t)(p.head >= 0 ? pad(p.head) : -1);
+    out->head = (int16_t)(p.head >= 0 ? pad(p.head) : 0);
     out->stones = (int16_t)(p.num_black + p.num_white);
     out->ko_key_col = (int16_t)(p.ko ? p.ko_col : 0);
     out->ko_idx = (int16_t)(p.ko ? pad(p.ko_idx) : 0);
