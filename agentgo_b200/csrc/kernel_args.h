@@ -12,7 +12,9 @@ namespace agb {
 // Device layout of a start position for the warp kernel: the board is padded to (N+2)x(N+2)
 // with a border of colour 3, so no neighbour access needs a bounds check.  Every index stored
 // in the state (links, roots, tails, head, last moves, ko point) is a padded index
-// p = (row+1)*(N+2) + (col+1).
+// p = (row+1)*(N+2) + (col+1).  The empty list uses cell 0 (a border cell) as its sentinel:
+// prev(first) = next(last) = 0 and head = 0 when the board is full (the reference's self-links
+// and SPACE_HEAD_NULL, Board.cpp:46-54, are translated by to_padded).
 constexpr int kMaxW = kMaxN + 2;
 constexpr int kMaxNP = kMaxW * kMaxW;
 struct PaddedPosition {
