@@ -184,6 +184,20 @@ struct WarpBoard {
         const bool cell_on = fCol(wc) != kBorder;
         const uint32_t wn = w0[cell_on ? cidx + off_nb : 0];        // w0[0] is a border cell
         const int ncol = fCol(wn);
+        if (MODE == kEvalBad) {
+            // rejection phase: a point with two or more empty neighbours that is not the ko point
+            // cannot be dying (its string keeps >= 2 liberties), an eye or a suicide.  When the
+            // FIRST candidate in draw order (cell 0) is of that kind it is accepted right away,
+            // before any string / liberty is looked at.
+            const int ne = __popc(__ballot_sync(kFull, ncol == 0) & nib);
+            const bool easy = ne >= 2 && ko_key != ((agent << 16) | cidx);
+            if (__ballot_sync(kFull, easy) & 1u) {
+                Eval z;
+                z.empty = true; z.kill = z.survive = z.chase = z.reserve = false;
+                z.bad = lane >= 4;
+                return z;
+            }
+        }
         const bool nb_stone = is_stone(ncol);
         const int root = nb_stone ? fA(wn) : -1 - (lane & 3);       // distinct negatives per direction
         const int hp = (int)(w1[nb_stone ? root : 0] & 0xffffu);
