@@ -218,3 +218,16 @@ def test_amaf_marks_match_oracle(built_lib):
         assert (w2 == w).all() and (sp2 == sp).all() and (sn2 == sn).all()
     with pytest.raises(ag.AgbError):
         ag.Engine(9, kernel=ag.KERNEL_THREAD).playouts_amaf(1, [(1, 1)], 10)
+
+
+@pytest.mark.parametrize("kernel", KERNELS)
+def test_move_cap_is_reported_as_fault(built_lib, kernel):
+    """The per-playout move cap is a fault detector only (the reference has no cap): hitting it
+    must surface as AGB_ERR_FAULT, never as a silent wrong score."""
+    e = ag.Engine(9, kernel=kernel, max_moves=10)
+    with pytest.raises(ag.AgbError) as ex:
+        e.playouts(ag.BLACK, None, 64)
+    assert ex.value.status == -5
+    # the engine stays usable afterwards
+    e2 = ag.Engine(9, kernel=kernel)
+    assert e2.playouts(ag.BLACK, None, 64)[4]["faults"] == 0
