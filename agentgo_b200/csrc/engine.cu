@@ -94,6 +94,7 @@ Engine::~Engine() {
     cudaFree(d_starts_); cudaFree(d_descs_); cudaFree(d_counters_); cudaFree(d_diffs_);
     cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_amaf_);
     if (h_pinned_) cudaFreeHost(h_pinned_);
+    if (h_stage_) cudaFreeHost(h_stage_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
     if (stream_) cudaStreamDestroy(stream_);
@@ -133,14 +134,23 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)S))) return st;
     if (want_diffs && (st = ensure(&d_diffs_, &cap_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P))) return st;
 
-    const void* start_src = starts.data();
-    if (!thread_kernel) {
-        padded_.resize(S);
-        for (int i = 0; i < S; i++) to_padded(starts[i], &padded_[i]);
-        start_src = padded_.data();
+    // inputs are staged in PINNED host memory and copied asynchronously on the engine's stream
+    const size_t desc_bytes = sizeof(StartDesc) * (size_t)S;
+    if (cap_stage_ < start_bytes + desc_bytes) {
+        if (h_stage_) cudaFreeHost(h_stage_);
+        h_stage_ = nullptr; cap_stage_ = 0;
+        AGB_CUDA(cudaMallocHost(&h_stage_, start_bytes + desc_bytes));
+        cap_stage_ = start_bytes + desc_bytes;
     }
-    AGB_CUDA(cudaMemcpyAsync(d_starts_, start_src, start_bytes, cudaMemcpyHostToDevice, stream_));
-    AGB_CUDA(cudaMemcpyAsync(d_descs_, descs.data(), sizeof(StartDesc) * (size_t)S, cudaMemcpyHostToDevice, stream_));
+    if (thread_kernel) {
+        memcpy(h_stage_, starts.data(), start_bytes);
+    } else {
+        PaddedPosition* pp = (PaddedPosition*)h_stage_;
+        for (int i = 0; i < S; i++) to_padded(starts[i], &pp[i]);
+    }
+    memcpy((char*)h_stage_ + start_bytes, descs.data(), desc_bytes);
+    AGB_CUDA(cudaMemcpyAsync(d_starts_, h_stage_, start_bytes, cudaMemcpyHostToDevice, stream_));
+    AGB_CUDA(cudaMemcpyAsync(d_descs_, (char*)h_stage_ + start_bytes, desc_bytes, cudaMemcpyHostToDevice, stream_));
     AGB_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(long long) * 3 * (size_t)S, stream_));
     AGB_CUDA(cudaMemsetAsync(d_small_, 0, kSmallWords * sizeof(unsigned long long), stream_));
 

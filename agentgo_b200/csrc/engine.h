@@ -59,7 +59,7 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     void* d_starts_ = nullptr; size_t cap_starts_ = 0;
     void* d_jump_ = nullptr;             // JumpTable (TinyMT32 T^16), built at create time
-    std::vector<PaddedPosition> padded_; // staging for the warp kernel's layout
+    void* h_stage_ = nullptr; size_t cap_stage_ = 0;   // pinned staging of the start positions + descriptors
     void* d_descs_ = nullptr; size_t cap_descs_ = 0;
     void* d_counters_ = nullptr; size_t cap_counters_ = 0;
     void* d_diffs_ = nullptr; size_t cap_diffs_ = 0;
