@@ -74,10 +74,15 @@ struct SmemArr {
 
 __device__ __forceinline__ int fA(uint32_t w) { return (int)(w & 1023u); }
 __device__ __forceinline__ int fB(uint32_t w) { return (int)((w >> 10) & 1023u); }
-__device__ __forceinline__ int fCol(uint32_t w) { return (int)((w >> 20) & 3u); }
+// device word layout: A | B<<10 | reserve<<20 | colour<<30 — the colour sits in the top two bits so
+// that it is one shift away and `empty` / `border` are plain compares on the word
+__device__ __forceinline__ int fCol(uint32_t w) { return (int)(w >> 30); }
+__device__ __forceinline__ bool isEmpty(uint32_t w) { return w < 0x40000000u; }
+__device__ __forceinline__ bool isBorder(uint32_t w) { return w >= 0xc0000000u; }
+constexpr uint32_t kReserveBit = 1u << 20;
 __device__ __forceinline__ bool is_stone(int col) { return ((col + 1) & 2) != 0; }   // 1 or 2
 __device__ __forceinline__ uint32_t pack0(int a, int b, int col) {
-    return (uint32_t)a | ((uint32_t)b << 10) | ((uint32_t)col << 20);
+    return (uint32_t)a | ((uint32_t)b << 10) | ((uint32_t)col << 30);
 }
 
 template <int N>
@@ -85,7 +90,7 @@ struct WarpBoard {
     static constexpr int W = N + 2;
     static constexpr int NP = W * W;
     static constexpr int NN = N * N;
-    SmemArr<uint32_t> w0;        // A | B<<10 | colour<<20 | reserve<<22   (field meaning: board_ops.h)
+    SmemArr<uint32_t> w0;        // A | B<<10 | reserve<<20 | colour<<30   (field meaning: board_ops.h)
     SmemArr<uint32_t> w1;        // hp | tail<<16 at root stones
     SmemArr<uint16_t> scratch;   // NN entries: compacted list of empty points (complex mode)
     int lane;
@@ -181,7 +186,7 @@ struct WarpBoard {
     __device__ __forceinline__ Eval eval_cells(int agent, int cidx) const {
         const unsigned nib = 15u << (lane & ~3);                    // this cell's four lanes
         const uint32_t wc = w0[cidx];
-        const bool cell_on = fCol(wc) != kBorder;
+        const bool cell_on = !isBorder(wc);
         const uint32_t wn = w0[cell_on ? cidx + off_nb : 0];        // w0[0] is a border cell
         const int ncol = fCol(wn);
         if (MODE == kEvalBad) {
@@ -214,7 +219,7 @@ struct WarpBoard {
             // kill, survive and chase all need a string next to an EMPTY cell that would be left
             // with 0 or 1 liberties (ecap / fcap: 0, eatari: 1); without one the three masks of
             // the neighbourhood phase are empty and nothing else matters (~70 % of the calls)
-            if (__ballot_sync(kFull, fCol(wc) == 0 && nb_stone && left <= 1) == 0) {
+            if (__ballot_sync(kFull, isEmpty(wc) && nb_stone && left <= 1) == 0) {
                 Eval z;
                 z.empty = z.kill = z.survive = z.chase = z.bad = z.reserve = false;
                 return z;
@@ -253,7 +258,7 @@ struct WarpBoard {
         const bool ko = ko_key == ((agent << 16) | cidx);           // :753-755
 
         Eval e;
-        e.empty = fCol(wc) == 0;
+        e.empty = isEmpty(wc);
         e.kill = ecap;                                              // :526-563
         e.survive = survive;
         e.chase = chase;
@@ -276,7 +281,7 @@ struct WarpBoard {
 #pragma unroll 1
             for (int base = 0; base < NP; base += 32) {
                 const int idx = base + lane;
-                const bool e = idx < NP && fCol(w0[idx]) == 0;
+                const bool e = idx < NP && isEmpty(w0[idx]);
                 const unsigned m = __ballot_sync(kFull, e);
                 if (e) scratch[n_e + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
                 n_e += __popc(m);
@@ -290,7 +295,7 @@ struct WarpBoard {
             const int idx = k < n_e ? (int)scratch[k] : 0;          // 0 is a border cell
             const Eval f = eval_cells<kEvalReserve>(agent, idx);
             const bool res = f.empty && f.reserve;
-            if (res && (lane & 3) == 0) w0[idx] |= (1u << 22);      // addReserve, :757-761
+            if (res && (lane & 3) == 0) w0[idx] |= kReserveBit;      // addReserve, :757-761
             reserved_total += __popc(__ballot_sync(kFull, res) & 0x11111111u);
         }
         __syncwarp();
@@ -302,7 +307,7 @@ struct WarpBoard {
 #pragma unroll 1
             for (int idx = head;;) {
                 const uint32_t w = w0[idx];
-                if (!((w >> 22) & 1u)) {
+                if (!(w & kReserveBit)) {
                     if (rnd == 0) { pick = idx; break; }
                     rnd--;
                 }
@@ -311,7 +316,7 @@ struct WarpBoard {
         }
         if (reserved_total) {                                       // resetReserve, :764-768
 #pragma unroll 1
-            for (int k = lane; k < n_e; k += 32) w0[scratch[k]] &= ~(1u << 22);
+            for (int k = lane; k < n_e; k += 32) w0[scratch[k]] &= ~kReserveBit;
             __syncwarp();
         }
         return pick;
@@ -362,7 +367,7 @@ struct WarpBoard {
                 const uint32_t cl = mod_small<N>(peek(2 * lane + 1));
                 const int idx = (int)(row * W + cl + (W + 1));
                 // the 100th draw is never accepted (:402-405)
-                const bool can = lane < B && count + lane + 1 != kEndingThreshold && fCol(w0[idx]) == 0;
+                const bool can = lane < B && count + lane + 1 != kEndingThreshold && isEmpty(w0[idx]);
                 unsigned cand = __ballot_sync(kFull, can);
                 // evaluate the empty candidates in draw order, 8 per round
 #pragma unroll 1
@@ -528,7 +533,7 @@ struct WarpBoard {
             if (d < 4) {
                 const int nb = __shfl_sync(kFull, nb_l, d);
                 const uint32_t v = w0[nb];
-                if (fCol(v) == 0) continue;                         // captured earlier in this put
+                if (isEmpty(v)) continue;                         // captured earlier in this put
                 const int sn = fA(v);
                 const uint32_t h = w1[sn] - 1u;                     // sn->hp -= 1
                 w1[sn] = h;
@@ -781,7 +786,7 @@ unsigned long long debug_violations() {
 void to_padded(const Position& p, PaddedPosition* out) {
     const int n = p.n, w = n + 2;
     auto pad = [&](int idx) { return (idx / n + 1) * w + (idx % n + 1); };
-    for (int i = 0; i < kMaxNP; i++) { out->w0[i] = (uint32_t)kBorder << 20; out->w1[i] = 0; }
+    for (int i = 0; i < kMaxNP; i++) { out->w0[i] = (uint32_t)kBorder << 30; out->w1[i] = 0; }
     for (int idx = 0; idx < n * n; idx++) {
         const uint32_t v0 = p.w0[idx], v1 = p.w1[idx];
         const int col = (int)((v0 >> 20) & 3u);
@@ -791,7 +796,7 @@ void to_padded(const Position& p, PaddedPosition* out) {
             if (a == idx) pa = 0;
             if (b == idx) pb = 0;
         }
-        out->w0[pad(idx)] = (uint32_t)pa | ((uint32_t)pb << 10) | ((uint32_t)col << 20);
+        out->w0[pad(idx)] = (uint32_t)pa | ((uint32_t)pb << 10) | ((uint32_t)col << 30);
         const bool is_root = col != 0 && a == idx;                  // hp/tail are meaningful at roots only
         out->w1[pad(idx)] = is_root ? ((v1 & 0xffffu) | ((uint32_t)pad((int)(v1 >> 16)) << 16)) : 0u;
     }
