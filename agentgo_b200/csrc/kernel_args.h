@@ -11,16 +11,30 @@ namespace agb {
 
 // Device layout of a start position for the warp kernel: the board is padded to (N+2)x(N+2)
 // with a border of colour 3, so no neighbour access needs a bounds check.  Every index stored
-// in the state (links, roots, tails, head, last moves, ko point) is a padded index
-// p = (row+1)*(N+2) + (col+1).  The empty list uses cell 0 (a border cell) as its sentinel:
-// prev(first) = next(last) = 0 and head = 0 when the board is full (the reference's self-links
-// and SPACE_HEAD_NULL, Board.cpp:46-54, are translated by to_padded).
+// in the state (links, roots, tails, last moves, ko point) is a padded index
+// p = (row+1)*(N+2) + (col+1).
+//
+//   w0 = A | B<<16 | colour<<30       (A and B are the two 16-bit halves of the word, so links and
+//                                      labels are rewritten with 16-bit stores, no read-modify-write)
+//        stone:  A = root index of its string,  B = next stone in the string (kNilP = end)
+//        empty:  A = slot of the point in `elist`, B = 0
+//   w1 = hp | tail<<16                at root stones
+//
+// The reference's doubly linked list of empty points (Board::space_list; removal Board.cpp:105-118,
+// head insertion per captured stone :311-321) is only ever OBSERVED by the ordered walk of
+// getRandomPieceComplex (:445-470).  Its order is "captured stones, latest first, then the
+// survivors of the initial list", so the device keeps it as an append-only array: list order =
+// elist[n_el-1], ..., elist[0] without the dead entries.  An entry k naming cell c is alive iff
+// c is empty and A(c) == k; filling a point costs nothing, a capture appends.
 constexpr int kMaxW = kMaxN + 2;
 constexpr int kMaxNP = kMaxW * kMaxW;
+constexpr int kNilP = 511;
+constexpr int kElistCap = 512;             // entries in shared memory; compacted when full
 struct PaddedPosition {
     uint32_t w0[kMaxNP];
     uint32_t w1[kMaxNP];
-    int16_t head, stones, ko_key_col, ko_idx, last[2], ending, pad;
+    uint32_t elist_w[(kMaxNN + 1) / 2];    // n_el 16-bit entries
+    int16_t n_el, stones, ko_key_col, ko_idx, last[2], ending, pad;
 };
 
 // GF(2) jump-ahead table of TinyMT32: T^k split by state nibble (k = jump_steps(), the number of

@@ -72,37 +72,44 @@ struct SmemArr {
 };
 #endif
 
-__device__ __forceinline__ int fA(uint32_t w) { return (int)(w & 1023u); }
-__device__ __forceinline__ int fB(uint32_t w) { return (int)((w >> 10) & 1023u); }
-// device word layout: A | B<<10 | reserve<<20 | colour<<30 — the colour sits in the top two bits so
-// that it is one shift away and `empty` / `border` are plain compares on the word
+// device word layout (kernel_args.h): A | B<<16 | colour<<30.  A and B are the 16-bit halves of the
+// word, so labels and links are rewritten with 16-bit stores; the colour sits in the top two bits so
+// that it is one shift away and `empty` / `border` are plain compares on the word.
+__device__ __forceinline__ int fA(uint32_t w) { return (int)(w & 0xffffu); }
+__device__ __forceinline__ int fB(uint32_t w) { return (int)((w >> 16) & 511u); }
+__device__ __forceinline__ int fBh(uint32_t hi) { return (int)(hi & 511u); }          // from the high half
 __device__ __forceinline__ int fCol(uint32_t w) { return (int)(w >> 30); }
 __device__ __forceinline__ bool isEmpty(uint32_t w) { return w < 0x40000000u; }
 __device__ __forceinline__ bool isBorder(uint32_t w) { return w >= 0xc0000000u; }
-constexpr uint32_t kReserveBit = 1u << 20;
 __device__ __forceinline__ bool is_stone(int col) { return ((col + 1) & 2) != 0; }   // 1 or 2
 __device__ __forceinline__ uint32_t pack0(int a, int b, int col) {
-    return (uint32_t)a | ((uint32_t)b << 10) | ((uint32_t)col << 30);
+    return (uint32_t)a | ((uint32_t)b << 16) | ((uint32_t)col << 30);
 }
+// high half of a stone's word: colour and next-in-string link
+__device__ __forceinline__ uint16_t packHi(int b, int col) { return (uint16_t)((uint32_t)b | ((uint32_t)col << 14)); }
+constexpr uint32_t kResFlag = 0x8000u;     // elist entry: point is reserved in the current complex-mode call
 
 template <int N>
 struct WarpBoard {
     static constexpr int W = N + 2;
     static constexpr int NP = W * W;
     static constexpr int NN = N * N;
-    SmemArr<uint32_t> w0;        // A | B<<10 | reserve<<20 | colour<<30   (field meaning: board_ops.h)
+    SmemArr<uint32_t> w0;        // A | B<<16 | colour<<30   (field meaning: kernel_args.h)
+    SmemArr<uint16_t> h0;        // the same words as 16-bit halves: h0[2i] = A, h0[2i+1] = B | colour<<14
     SmemArr<uint32_t> w1;        // hp | tail<<16 at root stones
-    SmemArr<uint16_t> scratch;   // NN entries: compacted list of empty points (complex mode)
+    SmemArr<uint16_t> elist;     // kElistCap entries: the empty list as an append-only array (kernel_args.h)
+    SmemArr<uint16_t> cbuf;      // 8 entries: candidates of one rejection round
     int lane;
     int off_nb;          // offset of this lane's orthogonal neighbour (dir = lane & 3: up, left, down, right)
     int off_dg;          // offset of this lane's diagonal
     int off_cell;        // offset of this lane's cell in the 3x3 block around a point (cell = lane >> 2)
-    int head;            // first empty point, 0 (the sentinel cell) = none
+    int n_el;            // entries in elist (dead ones included)
+    int n_dead;          // >= 0: complex mode lasts, elist holds no stale entries other than n_dead
+                         //       zeroed ones (put maintains it); -1: stale entries are validated lazily
     int stones;          // num_black + num_white (only the sum is ever read on this path)
     int ko_key;          // exist_compete ? compete colour<<16 | idx : -1
     int last0, last1;    // last_move[colour-1] as idx, -1 = none
     int ending;          // game_ending
-    int n_e;             // >= 0: scratch[0..n_e) lists the empty points (kept while complex mode lasts); -1: stale
     // --- random numbers: a ring of pre-generated rand() values (see refill) ---
     SmemArr<uint16_t> ring;      // kRing entries, entry (p & (kRing-1)) holds draw number p of this playout
     uint32_t g0, g1, g2, g3;     // generator state at draw number gen_end (warp-uniform)
@@ -267,35 +274,49 @@ struct WarpBoard {
         return e;
     }
 
-    // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags): the empty points
-    // are compacted with ballots, then evaluated 8 per round with eval_cells; the ordered walk
-    // that maps rnd to a point follows the empty list and is warp-uniform.
+    // Drop the dead entries of elist, keeping the order.  Entry k naming cell c is alive iff c is
+    // empty and A(c) == k (a zeroed entry names the border cell 0).  In place: a round reads 32
+    // entries and then writes at or below where it read.
+    __device__ __forceinline__ void compact() {
+        int out = 0;
+#pragma unroll 1
+        for (int base = 0; base < n_el; base += 32) {
+            const int k = base + lane;
+            const uint32_t c = k < n_el ? ((uint32_t)elist[k] & 0x7fffu) : 0u;
+            const uint32_t w = w0[(int)c];
+            const bool live = isEmpty(w) && fA(w) == k;
+            const unsigned m = __ballot_sync(kFull, live);
+            __syncwarp();
+            if (live) {
+                const int o = out + __popc(m & ((1u << lane) - 1u));
+                elist[o] = (uint16_t)c;
+                h0[2 * (int)c] = (uint16_t)o;
+            }
+            out += __popc(m);
+        }
+        n_el = out;
+        if (n_dead > 0) n_dead = 0;
+        __syncwarp();
+    }
+
+    // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags, :419-433): the
+    // entries of elist are evaluated 8 per round with eval_cells and flagged in place.  Pass 2
+    // (:445-470, the rnd-th unreserved point in list order) counts 32 entries per round from the
+    // end of the array.
     __device__ __forceinline__ int random_piece_complex(int agent) {
         const int spaces = NN - stones;
         if (spaces == 0) return -1;
-        if (n_e < 0) {
-            // compact the empty points with ballots (any order).  Complex mode is sticky
-            // (game_ending, :348-351), so the list is then maintained by put / kill_string
-            // instead of being rebuilt from all (N+2)^2 cells on each of the ~50 following calls.
-            n_e = 0;
-#pragma unroll 1
-            for (int base = 0; base < NP; base += 32) {
-                const int idx = base + lane;
-                const bool e = idx < NP && isEmpty(w0[idx]);
-                const unsigned m = __ballot_sync(kFull, e);
-                if (e) scratch[n_e + __popc(m & ((1u << lane) - 1u))] = (uint16_t)idx;
-                n_e += __popc(m);
-            }
-            __syncwarp();
-        }
+        // Complex mode is sticky (game_ending, :348-351): the array is made dense once and then
+        // kept current by put (zeroes the entry) and kill_string (appends).
+        if (n_dead < 0 || 4 * n_dead > n_el) { n_dead = 0; compact(); }
         int reserved_total = 0;
 #pragma unroll 1
-        for (int base = 0; base < n_e; base += 8) {
+        for (int base = 0; base < n_el; base += 8) {
             const int k = base + (lane >> 2);
-            const int idx = k < n_e ? (int)scratch[k] : 0;          // 0 is a border cell
+            const int idx = k < n_el ? (int)((uint32_t)elist[k] & 0x7fffu) : 0;     // 0 is a border cell
             const Eval f = eval_cells<kEvalReserve>(agent, idx);
             const bool res = f.empty && f.reserve;
-            if (res && (lane & 3) == 0) w0[idx] |= kReserveBit;      // addReserve, :757-761
+            if (f.empty && (lane & 3) == 0) elist[k] = (uint16_t)((uint32_t)idx | (res ? kResFlag : 0u));   // addReserve, :757-761
             reserved_total += __popc(__ballot_sync(kFull, res) & 0x11111111u);
         }
         __syncwarp();
@@ -305,19 +326,19 @@ struct WarpBoard {
             int rnd = (int)(peek(0) % (uint32_t)range);
             pos++;
 #pragma unroll 1
-            for (int idx = head;;) {
-                const uint32_t w = w0[idx];
-                if (!(w & kReserveBit)) {
-                    if (rnd == 0) { pick = idx; break; }
-                    rnd--;
+            for (int top = n_el - 1; top >= 0; top -= 32) {
+                const int k = top - lane;                           // lane order = list order
+                const uint32_t ent = k >= 0 ? (uint32_t)elist[k] : 0u;
+                const bool ok = ent - 1u < 0x7fffu;                 // alive and not reserved
+                const unsigned m = __ballot_sync(kFull, ok);
+                const int c = __popc(m);
+                if (rnd < c) {
+                    const bool hit = ok && __popc(m & ((1u << lane) - 1u)) == rnd;
+                    pick = (int)__shfl_sync(kFull, ent, __ffs(__ballot_sync(kFull, hit)) - 1);
+                    break;
                 }
-                idx = fB(w);
+                rnd -= c;
             }
-        }
-        if (reserved_total) {                                       // resetReserve, :764-768
-#pragma unroll 1
-            for (int k = lane; k < n_e; k += 32) w0[scratch[k]] &= ~kReserveBit;
-            __syncwarp();
         }
         return pick;
     }
@@ -334,7 +355,7 @@ struct WarpBoard {
             else complex_mode = true;
         }
         if (!complex_mode) {
-            n_e = -1;                                               // scratch is reused below
+            n_dead = -1;                                            // put stops maintaining elist
             const int lm = agent == 1 ? last1 : last0;              // opponent's last move
             if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
                 const Eval f = eval_cells<kEvalAll>(agent, lm + off_cell);
@@ -374,11 +395,11 @@ struct WarpBoard {
                 while (cand) {
                     const int rank = __popc(cand & ((1u << lane) - 1u));
                     const bool mine = ((cand >> lane) & 1u) && rank < 8;
-                    if (mine) scratch[rank] = (uint16_t)(idx | (lane << 9));
+                    if (mine) cbuf[rank] = (uint16_t)(idx | (lane << 9));
                     __syncwarp();
                     const int ncand = min(8, __popc(cand));
                     const int cell = lane >> 2;
-                    const uint32_t entry = cell < ncand ? scratch[cell] : 0u;     // 0 = a border cell
+                    const uint32_t entry = cell < ncand ? cbuf[cell] : 0u;        // 0 = a border cell
                     const Eval e = eval_cells<kEvalBad>(agent, (int)(entry & 511u));
                     const unsigned good = __ballot_sync(kFull, cell < ncand && !e.bad);
                     if (good) {
@@ -397,55 +418,36 @@ struct WarpBoard {
         return random_piece_complex(agent);
     }
 
-    // Board::killSetNode, Board.cpp:293-339 (warp-uniform)
+    // Board::killSetNode, Board.cpp:293-339.  The walk is warp-uniform; the four neighbours of each
+    // captured stone are looked at by lanes 0..3 (increments commute, so they are atomics).
     __device__ __forceinline__ void kill_string(int root) {
         const bool single = (int)(w1[root] >> 16) == root;
+        const int agent = fCol(w0[root]);                           // colour of the captured string
 #pragma unroll 1
-        for (int k = root; k != kNil;) {
-            const uint32_t w = w0[k];
-            const int nx = fB(w);
-            const int agent = fCol(w);
+        for (int k = root; k != kNilP;) {
+            const int nx = fBh(h0[2 * k + 1]);
             stones--;
-            w0[k] = pack0(0, head, 0);                              // push at the list head, :311-321
-            w0[head] = (w0[head] & ~1023u) | (uint32_t)k;           // (head == 0: the sentinel)
-            head = k;
-            if (n_e >= 0) { scratch[n_e] = (uint16_t)k; n_e++; }    // keep the list of empties current
-#pragma unroll
-            for (int d = 0; d < 4; d++) {                           // one liberty back, :323-326
-                const uint32_t v = w0[k + (d == 0 ? -W : (d == 1 ? -1 : (d == 2 ? W : 1)))];
-                if (fCol(v) == 3 - agent) w1[fA(v)] += 1u;
-            }
+            if (n_el == kElistCap) compact();                       // stale entries are dropped (never in complex mode)
+            elist[n_el] = (uint16_t)k;                              // push at the list head, :311-321
+            w0[k] = (uint32_t)n_el;                                 // empty, A = slot
+            n_el++;
+            const uint32_t v = w0[k + off_nb];                      // one liberty back, :323-326
+            if (lane < 4 && fCol(v) == 3 - agent) atomicAdd(&w1[fA(v)], 1u);
             if (single) ko_key = (agent << 16) | k;                 // :328-333
             k = nx;
         }
+        __syncwarp();
     }
 
-    // Board::put, Board.cpp:68-177 (warp-uniform; the point is empty)
+    // Board::put, Board.cpp:68-177 (warp-uniform; the point is empty).  Nothing is unlinked: the
+    // entry of the point in elist dies by itself (kernel_args.h); only while complex mode lasts it
+    // is zeroed, so that the array stays free of stale entries.
     __device__ __forceinline__ void put(int agent, int idx) {
         stones++;
         ko_key = -1;
-        {
-            // unlink from the empty list (:105-118).  On the device the list uses cell 0 (a border
-            // cell) as sentinel instead of the reference's self-links: prev(first) = next(last) = 0,
-            // so removal and head insertion need no case distinction.
-            const uint32_t w = w0[idx];
-            const int sp = fA(w), sx = fB(w);
-            w0[sp] = (w0[sp] & ~(1023u << 10)) | ((uint32_t)sx << 10);
-            w0[sx] = (w0[sx] & ~1023u) | (uint32_t)sp;
-            if (sp == 0) head = sx;
-        }
-        if (n_e >= 0) {                                             // keep the list of empties current
-#pragma unroll 1
-            for (int base = 0; base < n_e; base += 32) {
-                const int k = base + lane;
-                const unsigned m = __ballot_sync(kFull, k < n_e && scratch[k] == idx);
-                if (m) {
-                    scratch[base + __ffs(m) - 1] = scratch[n_e - 1];
-                    n_e--;
-                    break;
-                }
-            }
-            __syncwarp();
+        if (n_dead >= 0) {
+            elist[h0[2 * idx]] = 0;
+            n_dead++;
         }
         // lane d (mod 4) looks at neighbour d (up, left, down, right): colour, string, liberties
         const int dl = lane & 3;
@@ -477,7 +479,7 @@ struct WarpBoard {
             // current string to the neighbour's, SetNode.cpp:78-82), hp = sum(hp_i - mult_i) + own.
             if (lane < 4 && enemy_l && first) w1[root_l] = h_l - (uint32_t)mult;   // sn->hp -= 1 per adjacency
             if (fr_mask == 0) {
-                w0[idx] = pack0(idx, kNil, agent);                  // SetNode::init, SetNode.cpp:31-44
+                w0[idx] = pack0(idx, kNilP, agent);                 // SetNode::init, SetNode.cpp:31-44
                 w1[idx] = (uint32_t)hp_self | ((uint32_t)idx << 16);
             } else {
                 const int fk = __shfl_sync(kFull, root_l, 31 - __clz(fr_mask));
@@ -487,8 +489,8 @@ struct WarpBoard {
                 const int target = lower ? prev : idx;
                 const int tail_l = (int)(h_l >> 16);
                 const bool own_l = lane < 4 && frnd_l && first;
-                if (own_l) w0[tail_l] = (w0[tail_l] & ~(1023u << 10)) | ((uint32_t)target << 10);
-                w0[idx] = pack0(fk, kNil, agent);
+                if (own_l) h0[2 * tail_l + 1] = packHi(target, agent);
+                w0[idx] = pack0(fk, kNilP, agent);
                 w1[fk] = (uint32_t)hp_total | ((uint32_t)idx << 16);
                 // strings F_1..F_(k-1) are relabelled to Fk (:284-289)
                 const unsigned others = fr_mask & (fr_mask - 1u) ? fr_mask & ~(1u << (31 - __clz(fr_mask))) : 0u;
@@ -498,10 +500,9 @@ struct WarpBoard {
                     const int t1 = (int)(__shfl_sync(kFull, h_l, d1) >> 16);
 #pragma unroll 1
                     for (int sidx = __shfl_sync(kFull, root_l, d1);;) {
-                        const uint32_t w = w0[sidx];
-                        w0[sidx] = (w & ~1023u) | (uint32_t)fk;
+                        h0[2 * sidx] = (uint16_t)fk;
                         if (sidx == t1) break;
-                        sidx = fB(w);
+                        sidx = fBh(h0[2 * sidx + 1]);
                     }
                 } else if (others) {
                     // two or three strings: each is walked by its own lane
@@ -510,10 +511,9 @@ struct WarpBoard {
 #pragma unroll 1
                     while (__ballot_sync(kFull, walk)) {
                         if (walk) {
-                            const uint32_t w = w0[sidx];
-                            w0[sidx] = (w & ~1023u) | (uint32_t)fk;
+                            h0[2 * sidx] = (uint16_t)fk;
                             walk = sidx != tail_l;
-                            sidx = fB(w);
+                            sidx = fBh(h0[2 * sidx + 1]);
                         }
                     }
                 }
@@ -521,7 +521,7 @@ struct WarpBoard {
             __syncwarp();
         } else {
         // SLOW PATH (a capture happens): the reference's sequential order matters
-        w0[idx] = pack0(idx, kNil, agent);                          // SetNode::init, SetNode.cpp:31-44
+        w0[idx] = pack0(idx, kNilP, agent);                         // SetNode::init, SetNode.cpp:31-44
         w1[idx] = (uint32_t)idx << 16;
         unsigned todo = (__ballot_sync(kFull, st_l) & 15u) | 16u;
         // up, left, down, right (:129-164), then the stone's own string (:165-167) as step 4
@@ -546,12 +546,11 @@ struct WarpBoard {
                         const uint32_t h2 = w1[s2];
                         const int t1 = (int)(h >> 16);
                         w1[sn] = ((h + h2) & 0xffffu) | (h2 & 0xffff0000u);
-                        w0[t1] = (w0[t1] & ~(1023u << 10)) | ((uint32_t)s2 << 10);
+                        h0[2 * t1 + 1] = packHi(s2, agent);
 #pragma unroll 1
-                        for (int k = s2; k != kNil;) {
-                            const uint32_t w = w0[k];
-                            w0[k] = (w & ~1023u) | (uint32_t)sn;
-                            k = fB(w);
+                        for (int k = s2; k != kNilP;) {
+                            h0[2 * k] = (uint16_t)sn;
+                            k = fBh(h0[2 * k + 1]);
                         }
                     }
                 }
@@ -588,12 +587,12 @@ struct WarpBoard {
     }
 };
 
-// per-warp shared memory in words: w0[NP], w1[NP], scratch[NN] (16 bit) rounded to 32 words,
-// then the ring of kRing 16-bit draws
+// per-warp shared memory in words: w0[NP], w1[NP], elist[kElistCap] and cand[8] (16 bit), rounded
+// to 32 words, then the ring of kRing 16-bit draws
 template <int N>
 struct BoardWords {
     static constexpr int NP = (N + 2) * (N + 2);
-    static constexpr int board = ((2 * NP + (N * N + 1) / 2 + 31) / 32) * 32;
+    static constexpr int board = ((2 * NP + kElistCap / 2 + 4 + 31) / 32) * 32;
     static constexpr int value = board + WarpBoard<N>::kRing / 2;
     static constexpr int kAmafLog = 80;                     // first plays with cstep <= 40: at most 78
     static constexpr int value_amaf = value + kAmafLog / 2;
@@ -613,10 +612,12 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
     uint16_t* amaf_log = reinterpret_cast<uint16_t*>(base + BoardWords<N>::value);   // AMAF only
     bd.w0.p = base;
     bd.w1.p = base + WB::NP;
-    bd.scratch.p = reinterpret_cast<uint16_t*>(base + 2 * WB::NP);
+    bd.h0.p = reinterpret_cast<uint16_t*>(base);
+    bd.elist.p = reinterpret_cast<uint16_t*>(base + 2 * WB::NP);
+    bd.cbuf.p = bd.elist.p + kElistCap;
     bd.ring.p = reinterpret_cast<uint16_t*>(base + BoardWords<N>::board);
 #ifdef AGB_CHECK_BOUNDS
-    bd.w0.n = WB::NP; bd.w1.n = WB::NP; bd.scratch.n = WB::NN; bd.ring.n = WB::kRing;
+    bd.w0.n = WB::NP; bd.w1.n = WB::NP; bd.h0.n = 2 * WB::NP; bd.elist.n = kElistCap; bd.cbuf.n = 8; bd.ring.n = WB::kRing;
 #endif
     bd.init_lane(lane);
 
@@ -641,7 +642,12 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             bd.w0[i] = pos.w0[i];
             bd.w1[i] = pos.w1[i];
         }
-        bd.head = pos.head;
+        {
+            uint32_t* ew = base + 2 * WB::NP;                       // elist, two entries per word
+#pragma unroll 1
+            for (int i = lane; i < (WB::NN + 1) / 2; i += 32) ew[i] = pos.elist_w[i];
+        }
+        bd.n_el = pos.n_el;
         bd.stones = pos.stones;
         bd.ko_key = pos.ko_key_col > 0 ? ((pos.ko_key_col << 16) | pos.ko_idx) : -1;
         bd.last0 = pos.last[0];
@@ -649,7 +655,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         bd.ending = pos.ending;
         bd.pos = 0;
         bd.gen_end = 0;
-        bd.n_e = -1;
+        bd.n_dead = -1;
         __syncwarp();
         {
             // tinymt32_init (RFC 8682)
@@ -791,16 +797,28 @@ void to_padded(const Position& p, PaddedPosition* out) {
         const uint32_t v0 = p.w0[idx], v1 = p.w1[idx];
         const int col = (int)((v0 >> 20) & 3u);
         const int a = (int)(v0 & 1023u), b = (int)((v0 >> 10) & 1023u);
-        int pa = pad(a), pb = (col != 0 && b == kNil) ? kNil : pad(b);
-        if (col == 0) {                 // empty list: self-links of the reference become the sentinel 0
-            if (a == idx) pa = 0;
-            if (b == idx) pb = 0;
-        }
-        out->w0[pad(idx)] = (uint32_t)pa | ((uint32_t)pb << 10) | ((uint32_t)col << 30);
-        const bool is_root = col != 0 && a == idx;                  // hp/tail are meaningful at roots only
+        if (col == 0) { out->w0[pad(idx)] = 0; continue; }         // the slot is filled in below
+        out->w0[pad(idx)] = (uint32_t)pad(a) | ((uint32_t)(b == kNil ? kNilP : pad(b)) << 16) | ((uint32_t)col << 30);
+        const bool is_root = a == idx;                              // hp/tail are meaningful at roots only
         out->w1[pad(idx)] = is_root ? ((v1 & 0xffffu) | ((uint32_t)pad((int)(v1 >> 16)) << 16)) : 0u;
     }
-    out->head = (int16_t)(p.head >= 0 ? pad(p.head) : 0);
+    // the reference's empty list, head first (self-link = last, Board.cpp:46-54), becomes the
+    // array elist read from its end
+    int order[kMaxNN], m = 0;
+    for (int idx = p.head; idx >= 0 && m < n * n;) {
+        order[m++] = idx;
+        const int nx = (int)((p.w0[idx] >> 10) & 1023u);
+        if (nx == idx) break;
+        idx = nx;
+    }
+    uint16_t* el = reinterpret_cast<uint16_t*>(out->elist_w);
+    for (int i = 0; i < (int)(sizeof(out->elist_w) / 2); i++) el[i] = 0;
+    for (int k = 0; k < m; k++) {
+        const int c = pad(order[m - 1 - k]);
+        el[k] = (uint16_t)c;
+        out->w0[c] = (uint32_t)k;
+    }
+    out->n_el = (int16_t)m;
     out->stones = (int16_t)(p.num_black + p.num_white);
     out->ko_key_col = (int16_t)(p.ko ? p.ko_col : 0);
     out->ko_idx = (int16_t)(p.ko ? pad(p.ko_idx) : 0);
