@@ -31,7 +31,8 @@ SYMBOLS = [
     "agb_get_board", "agb_check", "agb_count_score", "agb_export_state", "agb_playouts",
     "agb_playouts_amaf", "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
     "agb_set_allreduce", "agb_playouts_batch", "agb_genmove", "agb_measure_peaks",
-    "agb_debug_violations", "agb_attach_nccl", "agb_detach_nccl",
+    "agb_debug_violations", "agb_attach_nccl", "agb_detach_nccl", "agb_static_units", "agb_last_marks",
+    "agb_genmove_step", "agb_set_genmove_step",
 ]
 
 
@@ -45,7 +46,8 @@ class Config(C.Structure):
     _fields_ = [("board_size", C.c_int), ("device", C.c_int), ("kernel", C.c_int),
                 ("shard_rank", C.c_int), ("shard_count", C.c_int),
                 ("mat1", C.c_uint32), ("mat2", C.c_uint32), ("tmat", C.c_uint32),
-                ("max_moves", C.c_int), ("genmove_amaf", C.c_int)]
+                ("max_moves", C.c_int), ("genmove_amaf", C.c_int),
+                ("genmove_static", C.c_int), ("genmove_book", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -115,6 +117,10 @@ def lib():
     l.agb_genmove.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64,
                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                               C.POINTER(Stats)]
+    l.agb_static_units.argtypes = [vp, C.c_int, C.c_int, C.c_int, i64p, i64p]
+    l.agb_last_marks.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
+    l.agb_genmove_step.argtypes = [vp]
+    l.agb_set_genmove_step.argtypes = [vp, C.c_int]
     l.agb_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), C.POINTER(C.c_int)]
     l.agb_debug_violations.restype = C.c_longlong
@@ -172,13 +178,13 @@ class Engine:
     """
 
     def __init__(self, board_size=13, device=0, kernel=KERNEL_AUTO, shard_rank=0, shard_count=1,
-                 max_moves=0, genmove_amaf=0):
+                 max_moves=0, genmove_amaf=0, genmove_static=0, genmove_book=0):
         self._l = lib()
         cfg = Config()
         self._l.agb_default_config(C.byref(cfg))
         cfg.board_size, cfg.device, cfg.kernel = board_size, device, kernel
         cfg.shard_rank, cfg.shard_count, cfg.max_moves = shard_rank, shard_count, max_moves
-        cfg.genmove_amaf = genmove_amaf
+        cfg.genmove_amaf, cfg.genmove_static, cfg.genmove_book = genmove_amaf, genmove_static, genmove_book
         h = C.c_void_p()
         st = self._l.agb_create(C.byref(cfg), C.byref(h))
         if st:
@@ -312,6 +318,28 @@ class Engine:
         self._chk(self._l.agb_genmove(self._h, colour, P_per_candidate, P_root, seed_base,
                                       C.byref(row), C.byref(col), C.byref(is_pass), C.byref(st)))
         return (None if is_pass.value else (row.value, col.value)), st.as_dict()
+
+    def static_units(self, colour, row, col):
+        """-> (units_a, units_b): the static pattern marks of MyWorker::work (AgentGo.cpp:104-282)
+        for one candidate, total_mark += units_a*bonus_a + units_b*bonus_b.  Host only."""
+        ua, ub = C.c_int64(), C.c_int64()
+        self._chk(self._l.agb_static_units(self._h, colour, row, col, C.byref(ua), C.byref(ub)))
+        return ua.value, ub.value
+
+    def last_marks(self):
+        """total_mark of the last genmove as an (N, N) array, or None after a book move."""
+        out = np.zeros((self.n, self.n), dtype=np.float64)
+        r = self._l.agb_last_marks(self._h, _p(out, C.c_double), out.size)
+        self._chk(r)
+        return out if r else None
+
+    @property
+    def genmove_step(self):
+        return int(self._l.agb_genmove_step(self._h))
+
+    @genmove_step.setter
+    def genmove_step(self, v):
+        self._chk(self._l.agb_set_genmove_step(self._h, int(v)))
 
     def counters_dev(self):
         return self._l.agb_counters_dev(self._h)

@@ -59,6 +59,7 @@ struct StartDesc {
     int16_t agent;       // side the diff is computed for
     int16_t first;       // colour that moves first in the pair loop
     int32_t avrg_win;
+    int32_t amaf_class;  // which AMAF table this start accumulates into (Engine::genmove), else 0
 };
 
 // TinyMT32 (RFC 8682), one stream per playout; rand() := uint32 >> 17.

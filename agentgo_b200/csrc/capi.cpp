@@ -81,12 +81,14 @@ int agb_boardsize(agb_engine* h, int n) {
     if (!h) return AGB_ERR_INVALID;
     if (!agb::HostBoard::size_supported(n)) return h->e->fail(AGB_ERR_INVALID, "unsupported board size");
     h->e->board.reset(n);
+    h->e->genmove_step = 0;
     return AGB_OK;
 }
 
 int agb_clear_board(agb_engine* h) {
     if (!h) return AGB_ERR_INVALID;
     h->e->board.clear();
+    h->e->genmove_step = 0;                 /* MyGame::onClear, AgentGo.cpp:377 */
     return AGB_OK;
 }
 
@@ -183,6 +185,32 @@ int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
     return h->e->playouts_batch(pos, B, P, seed_base, first_position_id, wins, sum_pos, sum_neg,
                                 per_playout_diff, stats);
     AGB_GUARD_END(h)
+}
+
+int agb_static_units(const agb_engine* h, int colour, int row, int col, int64_t* units_a, int64_t* units_b) {
+    if (!h || !units_a || !units_b) return AGB_ERR_INVALID;
+    const int n = h->e->board.n();
+    if ((colour != AGB_BLACK && colour != AGB_WHITE) || row < 0 || col < 0 || row >= n || col >= n)
+        return AGB_ERR_INVALID;
+    if (h->e->board.colour_at(row * n + col) != 0) return AGB_ERR_OCCUPIED;
+    h->e->board.static_units(colour, row, col, units_a, units_b);
+    return AGB_OK;
+}
+
+int agb_last_marks(const agb_engine* h, double* total_mark, int cap) {
+    if (!h || !total_mark) return AGB_ERR_INVALID;
+    const int words = (int)h->e->last_marks.size();
+    if (cap < words) return AGB_ERR_INVALID;
+    memcpy(total_mark, h->e->last_marks.data(), sizeof(double) * (size_t)words);
+    return words;
+}
+
+int agb_genmove_step(const agb_engine* h) { return h ? h->e->genmove_step : AGB_ERR_INVALID; }
+
+int agb_set_genmove_step(agb_engine* h, int step) {
+    if (!h || step < 0) return AGB_ERR_INVALID;
+    h->e->genmove_step = step;
+    return AGB_OK;
 }
 
 int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_root, uint64_t seed_base,

@@ -123,7 +123,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     const bool thread_kernel = cfg.kernel == AGB_KERNEL_THREAD;
     if (want_amaf && thread_kernel)
         return fail(AGB_ERR_INVALID, "AMAF marks are implemented by the warp kernel only");
-    const size_t amaf_bytes = sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n());
+    const size_t amaf_bytes = sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n()) * (size_t)amaf_classes();
     if (want_amaf) {
         if ((st = ensure(&d_amaf_, &cap_amaf_, amaf_bytes))) return st;
         AGB_CUDA(cudaMemsetAsync(d_amaf_, 0, amaf_bytes, stream_));
@@ -206,7 +206,7 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
         int r = allreduce_(allreduce_ctx_, d_counters_, 3 * S, (void*)stream_);
         if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
         if (want_amaf_) {
-            r = allreduce_(allreduce_ctx_, d_amaf_, AGB_AMAF_WORDS(board.n()), (void*)stream_);
+            r = allreduce_(allreduce_ctx_, d_amaf_, AGB_AMAF_WORDS(board.n()) * amaf_classes(), (void*)stream_);
             if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
         }
     }
@@ -220,7 +220,7 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
         AGB_CUDA(cudaMemcpyAsync(diffs, d_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P_, cudaMemcpyDeviceToHost, stream_));
     if (amaf) {
         if (!want_amaf_) return fail(AGB_ERR_STATE, "the launch in flight did not record AMAF marks");
-        AGB_CUDA(cudaMemcpyAsync(amaf, d_amaf_, sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n()),
+        AGB_CUDA(cudaMemcpyAsync(amaf, d_amaf_, sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n()) * (size_t)amaf_classes(),
                                  cudaMemcpyDeviceToHost, stream_));
     }
     AGB_CUDA(cudaStreamSynchronize(stream_));
@@ -251,7 +251,9 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
 }
 
 int Engine::playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P, int avrg_win,
-                            uint64_t seed_base, uint32_t position_id, bool want_diffs, bool want_amaf) {
+                            uint64_t seed_base, uint32_t position_id, bool want_diffs, bool want_amaf,
+                            bool split_amaf) {
+    amaf_class_stones_.assign(1, 0);
     if (want_amaf && C == 0) return fail(AGB_ERR_INVALID, "AMAF marks exist in candidate mode only");
     if (colour != AGB_BLACK && colour != AGB_WHITE) return fail(AGB_ERR_INVALID, "bad colour");
     if (C < 0 || (C > 0 && !cand_rc) || P <= 0) return fail(AGB_ERR_INVALID, "bad candidates or P");
@@ -261,9 +263,10 @@ int Engine::playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P
     if (C == 0) {
         // root mode = MyGame::testAvrgWin (AgentGo.cpp:412-448): the mover plays first
         starts.push_back(board.position());
-        StartDesc d = {position_id, AGB_ROOT_CANDIDATE, (int16_t)colour, (int16_t)colour, avrg_win};
+        StartDesc d = {position_id, AGB_ROOT_CANDIDATE, (int16_t)colour, (int16_t)colour, avrg_win, 0};
         descs.push_back(d);
     } else {
+        if (split_amaf) amaf_class_stones_.clear();
         starts.reserve(C);
         for (int c = 0; c < C; c++) {
             const int row = cand_rc[2 * c], col = cand_rc[2 * c + 1];
@@ -271,7 +274,14 @@ int Engine::playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P
             if (board.colour_at(row * n + col) != 0) return fail(AGB_ERR_OCCUPIED, "candidate point occupied");
             // MyWorker::work (AgentGo.cpp:83): candidate played, then the enemy moves first (:300,310)
             starts.push_back(board.with_move(colour, row * n + col));
-            StartDesc d = {position_id, (uint32_t)c, (int16_t)colour, (int16_t)(3 - colour), avrg_win};
+            StartDesc d = {position_id, (uint32_t)c, (int16_t)colour, (int16_t)(3 - colour), avrg_win, 0};
+            if (split_amaf) {
+                const int stones = starts.back().num_black + starts.back().num_white;
+                size_t k = 0;
+                while (k < amaf_class_stones_.size() && amaf_class_stones_[k] != stones) k++;
+                if (k == amaf_class_stones_.size()) amaf_class_stones_.push_back(stones);
+                d.amaf_class = (int32_t)k;
+            }
             descs.push_back(d);
         }
     }
@@ -295,7 +305,7 @@ int Engine::playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t s
         const int colour = pos[b].to_move;
         if (colour != AGB_BLACK && colour != AGB_WHITE) return fail(AGB_ERR_INVALID, "bad to_move");
         starts.push_back(hb.position());
-        StartDesc d = {pid, AGB_ROOT_CANDIDATE, (int16_t)colour, (int16_t)colour, 0};
+        StartDesc d = {pid, AGB_ROOT_CANDIDATE, (int16_t)colour, (int16_t)colour, 0, 0};
         descs.push_back(d);
         owner.push_back(b);
     }
@@ -327,11 +337,12 @@ int Engine::playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t s
     return AGB_OK;
 }
 
-// MyGame::onMove, step > 4 branch (AgentGo.cpp:573-688), flat-MC terms only:
-//   avrg_win = testAvrgWin (:579), candidate filter (:586-592), playouts per candidate,
+// MyGame::onMove (AgentGo.cpp:451-692):
+//   step 1..4: opening book (:468-572, cfg.genmove_book, 13x13 only);
+//   then avrg_win = testAvrgWin (:579), candidate filter (:586-592), playouts per candidate,
 //   mc[i][j] = 100*index_c * sum(score), score = w >= 0 ? w : w*cnsv, cnsv = 2^(avrg_win*index_cnsv)
-//   (:99,:328,:340), argmax with first-wins ties in row-major order (:647-676).
-// Static heuristics (:104-282) and AMAF (:329-338) are outside the flat-MC path.
+//   (:99,:328,:340), static pattern marks (:104-282, cfg.genmove_static), AMAF (:329-338,
+//   cfg.genmove_amaf), argmax with first-wins ties in row-major order (:647-676).
 int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_base, int* row, int* col,
                     int* is_pass, agb_stats* stats) {
     if (colour != AGB_BLACK && colour != AGB_WHITE) return fail(AGB_ERR_INVALID, "bad colour");
@@ -340,6 +351,13 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
     const int n = board.n();
     agb_stats acc, st1;
     memset(&acc, 0, sizeof(acc));
+    genmove_step++;                                           // :466
+    last_marks.clear();
+    if (cfg.genmove_book && genmove_step <= 4 && board.book_move(row, col)) {
+        *is_pass = 0;
+        if (stats) *stats = acc;
+        return AGB_OK;
+    }
     int64_t w = 0, sp = 0, sn = 0;
     int st = playouts_launch(colour, nullptr, 0, P_root, 0, seed_base, 0, false);
     if (st) return st;
@@ -357,36 +375,40 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
         if (P_cand < 0) P_cand = (-P_cand + C - 1) / C;      // fixed budget per genmove, split over candidates
         const bool use_amaf = cfg.genmove_amaf != 0 && cfg.kernel != AGB_KERNEL_THREAD;
         std::vector<int64_t> amaf;
-        if (use_amaf) amaf.resize((size_t)AGB_AMAF_WORDS(n));
-        st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false, use_amaf);
+        st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false, use_amaf, use_amaf);
         if (st) return st;
+        if (use_amaf) amaf.resize((size_t)AGB_AMAF_WORDS(n) * (size_t)amaf_classes());
         if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1, use_amaf ? amaf.data() : nullptr))) return st;
         acc.device_ms += st1.device_ms; acc.playouts += st1.playouts; acc.moves += st1.moves;
         acc.rng_draws += st1.rng_draws; acc.kernel_launches += st1.kernel_launches;
         const double cnsv = std::pow(2.0, avrg_win * 0.01);  // index_cnsv = 0.01, AgentGo.cpp:25,99
-        // AMAF terms (:86-94,:329-338): decay table over the step of the first play, from the number
-        // of stones after the candidate is played; index_amaf_* defaults of :21-24, index_c = 1.
+        // AMAF terms (:86-94,:329-338): decay table over the step of the first play.  The table
+        // depends on the number of stones after the candidate is played, so the marks were
+        // accumulated per distinct stone count; index_amaf_* defaults of :21-24, index_c = 1.
         std::vector<double> amaf12((size_t)n * n, 0.0);
         if (use_amaf) {
             const int NN = n * n, S = AGB_AMAF_RANGE + 1;
-            const int num_piece = board.position().num_black + board.position().num_white + 1;
-            const double num_a = 1.0 / (40.0 - (39.0 / 180) * num_piece);
-            const double num_b = 0.3 - (0.3 / 180) * num_piece;
-            double tab[AGB_AMAF_RANGE];
-            for (int k = 0; k < AGB_AMAF_RANGE; k++) {
-                double v = 1 - std::pow(num_a * k, num_b);
-                if (!(v >= 0)) v = 0;               // also catches NaN (negative base on boards > 13x13)
-                else if (v > 1) v = 1;
-                tab[k] = v;
-            }
-            for (int q = 0; q < NN; q++) {
-                double a1 = 0, a2 = 0;
-                for (int sidx = 2; sidx <= AGB_AMAF_RANGE; sidx++) {
-                    const double t = 100.0 * tab[sidx - 1];
-                    a1 += t * ((double)amaf[((size_t)(0 * 2 + 0) * S + sidx) * NN + q] + cnsv * (double)amaf[((size_t)(0 * 2 + 1) * S + sidx) * NN + q]);
-                    a2 -= t * ((double)amaf[((size_t)(1 * 2 + 0) * S + sidx) * NN + q] + cnsv * (double)amaf[((size_t)(1 * 2 + 1) * S + sidx) * NN + q]);
+            for (int k = 0; k < amaf_classes(); k++) {
+                const int64_t* A = amaf.data() + (size_t)k * AGB_AMAF_WORDS(n);
+                const int num_piece = amaf_class_stones()[k];
+                const double num_a = 1.0 / (40.0 - (39.0 / 180) * num_piece);
+                const double num_b = 0.3 - (0.3 / 180) * num_piece;
+                double tab[AGB_AMAF_RANGE];
+                for (int t = 0; t < AGB_AMAF_RANGE; t++) {
+                    double v = 1 - std::pow(num_a * t, num_b);
+                    if (!(v >= 0)) v = 0;           // also catches NaN (negative base on boards > 13x13)
+                    else if (v > 1) v = 1;
+                    tab[t] = v;
                 }
-                amaf12[q] = a1 + a2;
+                for (int q = 0; q < NN; q++) {
+                    double a1 = 0, a2 = 0;
+                    for (int sidx = 2; sidx <= AGB_AMAF_RANGE; sidx++) {
+                        const double t = 100.0 * tab[sidx - 1];
+                        a1 += t * ((double)A[((size_t)(0 * 2 + 0) * S + sidx) * NN + q] + cnsv * (double)A[((size_t)(0 * 2 + 1) * S + sidx) * NN + q]);
+                        a2 -= t * ((double)A[((size_t)(1 * 2 + 0) * S + sidx) * NN + q] + cnsv * (double)A[((size_t)(1 * 2 + 1) * S + sidx) * NN + q]);
+                    }
+                    amaf12[q] += a1 + a2;
+                }
             }
         }
         // argmax over every eligible point in row-major order, first maximum wins (:647-676).
@@ -394,20 +416,29 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
         bool init = false;
         double best = 0;
         int c = 0;
+        last_marks.assign((size_t)n * n, 0.0);
+        const int bonus_a = (int)((double)P_cand * 1000.0);   // int(numset*index_a), :95, index_a = 1000 (:18)
+        const int bonus_b = (int)((double)P_cand * 1.0);      // int(numset*index_b), :96, index_b = 1 (:19)
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 const bool is_cand = c < C && cand[2 * c] == i && cand[2 * c + 1] == j;
                 double mark = 0;
                 if (is_cand) {
+                    if (cfg.genmove_static) {                 // :104-282, added before any playout term
+                        int64_t ua = 0, ub = 0;
+                        board.static_units(colour, i, j, &ua, &ub);
+                        mark = (double)(ua * bonus_a + ub * bonus_b);
+                    }
                     // total_mark gets every score once (:339) and mc again (:653)
-                    mark = 2.0 * 100.0 * ((double)csp[c] + cnsv * (double)csn[c]);
+                    mark += 2.0 * 100.0 * ((double)csp[c] + cnsv * (double)csn[c]);
                     c++;
                 }
+                if (!board.is_eligible(colour, i, j)) { last_marks[(size_t)i * n + j] = mark; continue; }
                 mark += amaf12[(size_t)i * n + j];                                      // :654-655
-                if (!board.is_eligible(colour, i, j)) continue;
+                last_marks[(size_t)i * n + j] = mark;
                 if (!init || mark > best) { best = mark; *row = i; *col = j; init = true; }
             }
-        *is_pass = 0;
+        *is_pass = init ? 0 : 1;                              // domove, :667,:688-691
     }
     if (stats) *stats = acc;
     return AGB_OK;

@@ -32,17 +32,27 @@ public:
     int launch(const std::vector<Position>& starts, const std::vector<StartDesc>& descs, int64_t P,
                uint64_t seed_base, bool want_diffs, bool shard_units, bool want_amaf = false);
     // waits, copies counters (and diffs) out.  Buffers are [n_starts] / [n_starts*P].
-    // amaf: [AGB_AMAF_WORDS(n)] or nullptr; only valid after a launch with want_amaf
+    // amaf: [amaf_classes() * AGB_AMAF_WORDS(n)] or nullptr; only valid after a launch with want_amaf
     int finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats,
                int64_t* amaf = nullptr);
 
     int playouts_launch(int colour, const int16_t* cand_rc, int C, int64_t P, int avrg_win,
-                        uint64_t seed_base, uint32_t position_id, bool want_diffs, bool want_amaf = false);
+                        uint64_t seed_base, uint32_t position_id, bool want_diffs, bool want_amaf = false,
+                        bool split_amaf = false);
+    // AMAF tables of the launch in flight / last launch.  The reference recomputes its decay table
+    // per candidate from the number of stones AFTER the candidate is played (AgentGo.cpp:86-94), so
+    // candidates that capture use another table: with split_amaf the marks are accumulated per
+    // distinct stone count (class k holds the candidates that leave amaf_class_stones()[k] stones).
+    int amaf_classes() const { return (int)amaf_class_stones_.size(); }
+    const std::vector<int>& amaf_class_stones() const { return amaf_class_stones_; }
     int playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t seed_base,
                        uint32_t first_position_id, int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
                        int16_t* diffs, agb_stats* stats);
     int genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_base, int* row, int* col,
                 int* is_pass, agb_stats* stats);
+
+    int genmove_step = 0;                // MyGame::step, AgentGo.cpp:353
+    std::vector<double> last_marks;      // total_mark of the last genmove (empty after a book move)
 
     void* counters_dev() const { return d_counters_; }
     cudaStream_t stream() const { return stream_; }
@@ -74,6 +84,7 @@ private:
     bool want_diffs_ = false;
     bool shard_units_ = false;
     bool want_amaf_ = false;
+    std::vector<int> amaf_class_stones_ = std::vector<int>(1, 0);
     LaunchInfo info_ = {0, 0, 0, ""};
     AllreduceFn allreduce_ = nullptr;
     void* allreduce_ctx_ = nullptr;

@@ -140,9 +140,10 @@ void MyGame::onMoved(int isW, int a, int b) {
     for (agb_engine* p : peers) agb_play(p, isW + 1, a, b);
 }
 
-// MyGame::onMove (AgentGo.cpp:449-693) without the 13x13 opening book of steps 1-4 (:468-572),
-// the static heuristics and the AMAF terms: avrg_win from root playouts, the
-// candidate filter, playouts per candidate, argmax — all inside agb_genmove.
+// MyGame::onMove (AgentGo.cpp:449-693): avrg_win from root playouts, the candidate filter,
+// playouts per candidate, argmax — all inside agb_genmove, which also holds the 13x13 opening
+// book of steps 1-4 (:468-572), the static pattern marks (:104-282) and the AMAF terms
+// (:329-338) behind agb_config::genmove_book / genmove_static / genmove_amaf.
 bool MyGame::onMove(int isW, int& a, int& b) {
     step += 1;
     int row = -1, col = -1, is_pass = 1;

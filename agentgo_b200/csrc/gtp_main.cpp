@@ -2,7 +2,8 @@
 // self-play driver for BASELINE.json configs[3] (device-timed genmove latency).
 //
 //   agentgo_gtp [--boardsize N] [--playouts P] [--total-playouts M] [--root-playouts R]
-//               [--device D] [--gpus N] [--seed S] [--kernel auto|thread|warp] [--amaf]
+//               [--device D] [--gpus N] [--seed S] [--kernel auto|thread|warp]
+//               [--amaf] [--static] [--book] [--reference-policy]
 //               [--selfplay [--max-moves K]]
 //
 //   --playouts P        playouts per candidate (reference: numset = 150, AgentGo.cpp:85)
@@ -11,6 +12,9 @@
 //   --gpus N            N GPUs of this box in one process: playouts sharded over N engines, counters
 //                       combined by one NCCL allreduce per evaluation (agb_attach_nccl)
 //   --amaf              add the AMAF terms amaf1 + amaf2 (AgentGo.cpp:329-338,654-655) to the marks
+//   --static            add the static pattern marks of MyWorker::work (AgentGo.cpp:104-282)
+//   --book              answer the first four genmoves from the 13x13 opening book (AgentGo.cpp:468-572)
+//   --reference-policy  all three: the complete MyGame::onMove of the reference
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -45,6 +49,9 @@ int main(int argc, char** argv) {
         else if (a == "--max-moves") max_moves = atoi(next("--max-moves"));
         else if (a == "--selfplay") selfplay = true;
         else if (a == "--amaf") cfg.genmove_amaf = 1;
+        else if (a == "--static") cfg.genmove_static = 1;
+        else if (a == "--book") cfg.genmove_book = 1;
+        else if (a == "--reference-policy") cfg.genmove_amaf = cfg.genmove_static = cfg.genmove_book = 1;
         else if (a == "--gpus") gpus = atoi(next("--gpus"));
         else if (a == "--kernel") {
             const std::string k = next("--kernel");

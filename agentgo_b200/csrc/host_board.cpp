@@ -31,6 +31,19 @@ void HostBoard::clear() {
     r.n_rt = n;
     r.clear();
     close(r);
+    memset(space_shadow_, 0, sizeof(space_shadow_));
+    sync_space_shadow();
+}
+
+// see space_shadow_: called after every change of the position
+void HostBoard::sync_space_shadow() {
+    const Ref r = open();
+    const int NN = nn();
+    for (int idx = 0; idx < NN; idx++)
+        if (r.col(idx) == 0) {
+            space_shadow_[idx][0] = (int16_t)r.A(idx);
+            space_shadow_[idx][1] = (int16_t)r.B(idx);
+        }
 }
 
 int HostBoard::play(int colour, int row, int col) {
@@ -42,6 +55,7 @@ int HostBoard::play(int colour, int row, int col) {
     if (r.col(idx) != 0) return -2;   // reference: AG_PANIC, Board.cpp:75-78
     r.put(colour, idx);
     close(r);
+    sync_space_shadow();
     return 0;
 }
 
@@ -133,6 +147,88 @@ Position HostBoard::with_move(int colour, int idx) const {
     r.put(colour, idx);
     copy.close(r);
     return copy.pos_;
+}
+
+// `mj->bd->data[row][col]` as the reference's compiled code reads it.  Two of the knight's-move
+// tests of MyWorker::work guard one point and read another (AgentGo.cpp:185-191, 217-223), so
+// `col` reaches -2..N and `row` reaches N: the read lands on the flat int array Board::data
+// (Board.h:41) or, past its end, on the members that follow it: num_black, num_white, space_head,
+// space_list[0..][2] (Board.h:42-45).  That is undefined behaviour in C++, but it is what both
+// the MSVC build and the g++ oracle do, and it decides marks on the last row.
+int HostBoard::data_at(int row, int col) const {
+    const int n = pos_.n, NN = n * n;
+    const int f = row * n + col;
+    if (f < 0) return 0;                                // not reachable from static_units
+    if (f < NN) return (int)((pos_.w0[f] >> 20) & 3u);
+    const int k = f - NN;
+    if (k == 0) return pos_.num_black;
+    if (k == 1) return pos_.num_white;
+    if (k == 2) return pos_.head;
+    const int e = (k - 3) >> 1;
+    return e < NN ? space_shadow_[e][(k - 3) & 1] : 0;
+}
+
+void HostBoard::static_units(int colour, int row, int col, int64_t* units_a, int64_t* units_b) const {
+    const int agent = colour, enemy = 3 - colour;
+    const int last = pos_.n - 1;                        // the literal 12 of the reference
+    int64_t ua = 0, ub = 0;
+    // on the board before the candidate is played (bd_copy, :81): :104-109
+    if (check(3, agent, row, col) == 1) ua -= 1;        // checkDying
+    if (no_sense(agent, row, col)) ua -= 1;             // checkNoSense
+    if (check(2, agent, row, col) == 1) ub += 1;        // checkSurvive
+    // everything below reads the board AFTER the candidate (and its captures), mj->bd (:83)
+    HostBoard after(*this);
+    after.play(agent, row, col);
+    auto in = [&](int v) { return v >= 0 && v <= last; };
+    // contact / diagonal / knight's-move terms, :111-240.  "Friend" is tested as data == agent+1:
+    // for black that is a WHITE stone (so the enemy branch is never reached), for white it is 3
+    // and never matches.  gr/gc: the point the guard tests; dr/dc: the point that is read.
+    struct Term { int gr, gc, dr, dc; };
+    static const Term terms[] = {
+        {0, -1, 0, -1}, {-1, 0, -1, 0}, {0, 1, 0, 1}, {1, 0, 1, 0},          // :111-141
+        {1, 1, 1, 1}, {1, -1, 1, -1}, {-1, 1, -1, 1}, {-1, -1, -1, -1},      // :143-174
+        {-1, 2, -1, 2},                                                      // :176-183
+        {-2, 1, 1, -2},                                                      // :184-191 (guard and read differ)
+        {-1, -2, -1, -2}, {-2, -1, -2, -1}, {1, 2, 1, 2},                    // :192-215
+        {2, -2, 2, 1},                                                       // :216-223 (guard and read differ)
+        {1, -2, 1, -2}, {2, -1, 2, -1},                                      // :224-239
+    };
+    for (const Term& t : terms) {
+        if (!(in(row + t.gr) && in(col + t.gc))) continue;
+        const int v = after.data_at(row + t.dr, col + t.dc);
+        if (v == agent + 1) ub += 1;
+        else if (v == enemy) ub -= 1;
+    }
+    // cut patterns, :241-282 (these compare with `agent`), each worth 20 * bonus_b
+    if (row - 1 >= 0 && row + 1 <= last && col - 1 >= 0 && col + 1 <= last) {
+        auto D = [&](int dr, int dc) { return after.data_at(row + dr, col + dc); };
+        if ((D(0, 1) == agent || D(0, -1) == agent || (D(-1, 1) == agent && D(-1, -1) == agent) ||
+             (D(1, 1) == agent && D(1, -1) == agent)) && D(-1, 0) == enemy && D(1, 0) == enemy) ub += 20;
+        if ((D(-1, 0) == agent || D(1, 0) == agent || (D(-1, 1) == agent && D(1, 1) == agent) ||
+             (D(-1, -1) == agent && D(1, -1) == agent)) && D(0, 1) == enemy && D(0, -1) == enemy) ub += 20;
+        if (D(1, 1) == agent && D(1, 0) == enemy && D(0, 1) == enemy && (D(0, -1) == agent || D(-1, 0) == agent)) ub += 20;
+        if (D(-1, 1) == agent && D(-1, 0) == enemy && D(0, 1) == enemy && (D(0, -1) == agent || D(1, 0) == agent)) ub += 20;
+        if (D(1, -1) == agent && D(1, 0) == enemy && D(0, -1) == enemy && (D(-1, 0) == agent || D(0, 1) == agent)) ub += 20;
+        if (D(-1, -1) == agent && D(-1, 0) == enemy && D(0, -1) == enemy && (D(0, 1) == agent || D(1, 0) == agent)) ub += 20;
+    }
+    *units_a = ua;
+    *units_b = ub;
+}
+
+bool HostBoard::book_move(int* row, int* col) const {
+    if (pos_.n != 13) return false;
+    // nine regions cut at rows/cols 4 and 9, :482-536
+    bool taken[9] = {false, false, false, false, false, false, false, false, false};
+    for (int i = 0; i < 13; i++)
+        for (int j = 0; j < 13; j++)
+            if (((pos_.w0[i * 13 + j] >> 20) & 3u) != 0)
+                taken[(i < 4 ? 0 : (i < 9 ? 1 : 2)) * 3 + (j < 4 ? 0 : (j < 9 ? 1 : 2))] = true;
+    // first free region in this order, :537-581
+    static const int order[8][3] = {{0, 3, 3}, {8, 9, 9}, {2, 3, 9}, {6, 9, 3}, {1, 3, 5}, {7, 9, 7}, {3, 7, 3}, {5, 5, 9}};
+    *row = 6; *col = 6;
+    for (const auto& o : order)
+        if (!taken[o[0]]) { *row = o[1]; *col = o[2]; break; }
+    return true;
 }
 
 int HostBoard::export_state(int32_t* out, int cap) const {

@@ -43,6 +43,15 @@ public:
     // canonical dump shared with the oracle (16 + 7*NN int32 words)
     int export_state(int32_t* out, int cap) const;
 
+    // Static pattern marks of MyWorker::work for the candidate (row, col) of `colour`
+    // (AgentGo.cpp:104-282), as integers: total_mark[row][col] receives
+    //     units_a * bonus_a + units_b * bonus_b,   bonus_x = int(numset * index_x)   (:95-96).
+    // Every quirk of the reference is kept (see the definition).  The point must be empty.
+    void static_units(int colour, int row, int col, int64_t* units_a, int64_t* units_b) const;
+    // The 13x13 opening book of MyGame::onMove for its first four calls (AgentGo.cpp:468-572).
+    // false when the board is not 13x13 (the book is made of 13x13 literals).
+    bool book_move(int* row, int* col) const;
+
     const Position& position() const { return pos_; }
     // copy of the position after `colour` plays idx (AgentGo.cpp:83)
     Position with_move(int colour, int idx) const;
@@ -52,7 +61,14 @@ private:
     Ref open() const;
     void close(const Ref& r);
     bool no_sense(int colour, int row, int col) const;
+    void sync_space_shadow();
+    int data_at(int row, int col) const;
     Position pos_;
+    // Board::space_list as the reference leaves it in memory: the links of the empty points are the
+    // live list (= pos_), those of occupied points keep the values they had when the point was
+    // taken (Board.cpp:105-118 does not clear them).  Only static_units looks at it, through the
+    // reference's out-of-range reads of Board::data (see data_at).
+    int16_t space_shadow_[kMaxNN][2];
 };
 
 }  // namespace agb

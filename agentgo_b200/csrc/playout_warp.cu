@@ -735,7 +735,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
                 if (valid && w != 0 && (is_agent || !agent_marked)) {
                     const uint32_t row = q / WB::W - 1, col = q % WB::W - 1;
                     const uint32_t slot = ((is_agent ? 0u : 2u) + (w < 0 ? 1u : 0u)) * (kAmafRange + 1) + (e >> 10);
-                    atomicAdd((unsigned long long*)&a.amaf[(size_t)slot * WB::NN + row * N + col],
+                    atomicAdd((unsigned long long*)&a.amaf[((size_t)d.amaf_class * (4 * (kAmafRange + 1)) + slot) * WB::NN + row * N + col],
                               (unsigned long long)(long long)w);
                 }
             }

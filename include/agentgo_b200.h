@@ -17,6 +17,8 @@
  *   MyWorker::work playout loop    AgentGo.cpp:285-327  agb_playouts   (C >= 1)
  *   MyGame::testAvrgWin            AgentGo.cpp:412-448  agb_playouts   (C == 0, "root mode")
  *   MyGame::onMove (step>4 branch) AgentGo.cpp:573-688  agb_genmove
+ *   MyGame::onMove (opening book)  AgentGo.cpp:468-572  agb_genmove   (cfg.genmove_book)
+ *   MyWorker::work static marks    AgentGo.cpp:104-282  agb_static_units, agb_genmove (cfg.genmove_static)
  *   Board::check*                  Board.cpp:480-755    agb_check
  *   Board::countScore              Board.cpp:910        agb_count_score
  *
@@ -94,7 +96,13 @@ typedef struct agb_config {
     int max_moves;       /* per-playout move cap, 0 => default (fault detector)    */
     int genmove_amaf;    /* agb_genmove: 0 flat MC only (default); 1 adds the AMAF terms
                             amaf1 + amaf2 of AgentGo.cpp:329-338,654-655                 */
+    int genmove_static;  /* agb_genmove: 1 adds the static pattern marks of MyWorker::work
+                            (AgentGo.cpp:104-282, agb_static_units) to every candidate       */
+    int genmove_book;    /* agb_genmove: 1 answers the first four calls after a clear_board from
+                            the reference's 13x13 opening book (AgentGo.cpp:468-572); ignored on
+                            other board sizes (the book is made of 13x13 literals)            */
 } agb_config;
+/* amaf + static + book = the complete MyGame::onMove of the reference */
 
 typedef struct agb_engine agb_engine;
 
@@ -223,16 +231,40 @@ int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
                        int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
                        int16_t* per_playout_diff, agb_stats* stats);
 
-/* GTP-compat genmove (AgentGo.cpp:573-688 without the static heuristics and
- * AMAF terms, which are outside the flat-MC path): root playouts -> avrg_win,
- * candidate filter, P playouts per candidate, argmax of
- * sum_pos + cnsv*sum_neg (plus amaf1 + amaf2 when cfg.genmove_amaf).  *is_pass = 1
+/* GTP-compat genmove (MyGame::onMove, AgentGo.cpp:451-692): root playouts -> avrg_win,
+ * candidate filter, P playouts per candidate, argmax of total_mark =
+ * 2*100*(sum_pos + cnsv*sum_neg), plus amaf1 + amaf2 when cfg.genmove_amaf, plus the static
+ * pattern marks when cfg.genmove_static; the first four calls come from the opening book when
+ * cfg.genmove_book (13x13).  With all three set and P = 150 / 500 this is the reference's move
+ * (tests/test_gpu_genmove_ref.py checks it against the reference's own onMove).  *is_pass = 1
  * when no candidate exists.  The move
  * is NOT played on the engine's board (the caller does, GTPAdapter.cpp:78).
  * P_per_candidate < 0: |P_per_candidate| is a fixed playout budget per genmove,
  * split evenly (rounded up) over the candidates.                              */
 int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_root,
                 uint64_t seed_base, int* row, int* col, int* is_pass, agb_stats* stats);
+
+/* Static pattern marks of MyWorker::work (AgentGo.cpp:104-282) for one candidate of `colour` on
+ * the engine's board, as the two integers of
+ *     total_mark[row][col] += units_a * bonus_a + units_b * bonus_b,
+ *     bonus_a = int(numset * index_a), bonus_b = int(numset * index_b)       (AgentGo.cpp:95-96,
+ *     index_a = 1000, index_b = 1 at :18-19; numset = playouts per candidate).
+ * units_a: -1 for checkDying, -1 for checkNoSense (:105-107).  units_b: +1 checkSurvive (:109), the
+ * contact / diagonal / knight's-move terms (:111-240) and 20 per cut pattern (:241-282).  The
+ * reference's quirks are part of the contract: "friend" is tested as data == agent+1 (for black
+ * that is a white stone, for white nothing), and two knight's-move tests read a different point
+ * than they guard (:185-191, 217-223), past the end of Board::data on the last row.  Host only.  */
+int agb_static_units(const agb_engine* h, int colour, int row, int col,
+                     int64_t* units_a, int64_t* units_b);
+
+/* total_mark of the last agb_genmove (N*N doubles, row-major; AgentGo.cpp:17,653-655): static
+ * marks + 2 x flat-MC term + amaf1 + amaf2 as configured; 0 where nothing was added.  Returns the
+ * number of doubles written, 0 when the last genmove was answered from the book, <0 on error.  */
+int agb_last_marks(const agb_engine* h, double* total_mark, int cap);
+/* number of agb_genmove calls since the last clear_board / boardsize (MyGame::step, AgentGo.cpp:353);
+ * agb_set_genmove_step overrides it (a host that replays a game sets it to the move count). */
+int agb_genmove_step(const agb_engine* h);
+int agb_set_genmove_step(agb_engine* h, int step);
 
 /* ---- diagnostics -------------------------------------------------------
  * Live micro-benchmarks of the two rates that bound the playout kernels:

@@ -45,6 +45,34 @@ stream() {
     echo "#line 1 \"oracle/ref_harness.cpp\""
     cat "$here/ref_harness.cpp"
 }
+# The reference's move selection (AgentGo.cpp:15-705: globals, MyJob, MyWorker::work with the static
+# pattern heuristics, MyGame::testAvrgWin / onMove with the opening book), 13x13 only (its literals).
+# Additional stream edits, each forced by the build or by the harness:
+#   6. lines 1-14 (Win32 includes, `using namespace TinyMT`) and 706-end (_tmain) are not streamed;
+#      TinyMT.h / TinyOP.h types come from ref_genmove_shim.h with a serial schedule
+#   7. `class X` -> `struct X` at line starts (the harness reads MyGame::step and calls onMove)
+#   8. one line inserted after AgentGo.cpp:288 and :419 (top of the two playout loops) that starts the
+#      injected per-playout TinyMT32 stream (the reference seeds libc rand() once per process)
+stream_genmove() {
+    stream 13 | sed -e '/^#line 1 "oracle\/ref_harness.cpp"/,$d'
+    cat "$here/ref_genmove_shim.h"
+    echo "#line 1 \"reference:GTPAdapter.h\""
+    tr -d '\r' < "$ref/AgentGo/GTPAdapter.h" | iconv -f GBK -t UTF-8 -c | sed -e 's/^#include ".*$//'
+    echo
+    echo "#line 15 \"reference:AgentGo.cpp\""
+    tr -d '\r' < "$ref/AgentGo/AgentGo.cpp" | iconv -f GBK -t UTF-8 -c | sed -n '15,705p' \
+      | sed -e 's/^class /struct /' \
+            -e 's/^\([[:space:]]*\)mj->bd->clone(bdnew);/&oracle_seed_candidate(oracle_job_index, ii);/' \
+            -e 's/^\([[:space:]]*\)bdtest.clone(bd);/&oracle_seed_root(ii);/'
+    echo
+    echo "#line 1 \"oracle/ref_harness.cpp\""
+    cat "$here/ref_harness.cpp"
+    echo "#line 1 \"oracle/ref_genmove_harness.cpp\""
+    cat "$here/ref_genmove_harness.cpp"
+}
+stream_genmove | "$CXX" -x c++ -std=c++11 -O2 -fPIC -shared -pthread -w \
+    -I "$here" -I "$here/../include" -o "$out/liboracle_ref_genmove_13.so" -
+echo "built $out/liboracle_ref_genmove_13.so"
 for n in 9 13 19; do
     stream "$n" | "$CXX" -x c++ -std=c++11 -O2 -fPIC -shared -pthread -w \
         -I "$here" -I "$here/../include" -o "$out/liboracle_ref_$n.so" -

@@ -201,3 +201,78 @@ class OracleBoard:
         if with_stats:
             return res + ({"moves": int(stat2[0]), "rng_draws": int(stat2[1])},)
         return res
+
+
+GENMOVE_LIB = os.path.join(REF_DIR, "liboracle_ref_genmove_13.so")
+
+
+def genmove_ref_available():
+    return os.path.exists(GENMOVE_LIB)
+
+
+class RefGame:
+    """The reference's own MyGame (AgentGo.cpp:351-705: opening book, testAvrgWin, candidate filter,
+    MyWorker::work with its static pattern heuristics, AMAF, argmax), 13x13 only, run with a serial
+    schedule and the injected per-playout TinyMT32 (oracle/ref_genmove_shim.h)."""
+    N = 13
+
+    def __init__(self):
+        key = ("genmove", 13)
+        if key not in _libs:
+            lib = C.CDLL(GENMOVE_LIB)
+            dp = C.POINTER(C.c_double)
+            lib.orc_gm_new.restype = C.c_void_p
+            lib.orc_gm_free.argtypes = [C.c_void_p]
+            lib.orc_gm_clear.argtypes = [C.c_void_p]
+            lib.orc_gm_play.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+            lib.orc_gm_step.argtypes = [C.c_void_p]
+            lib.orc_gm_set_step.argtypes = [C.c_void_p, C.c_int]
+            lib.orc_gm_genmove.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_int),
+                                           C.POINTER(C.c_int), dp, dp, dp, dp]
+            lib.orc_gm_static_mark.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64]
+            lib.orc_gm_static_mark.restype = C.c_double
+            _libs[key] = lib
+        self.lib = _libs[key]
+        self.h = self.lib.orc_gm_new()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.orc_gm_free(self.h)
+            self.h = None
+
+    def clear(self):
+        self.lib.orc_gm_clear(self.h)
+
+    def play(self, colour, row, col):
+        r = self.lib.orc_gm_play(self.h, colour, row, col)
+        if r:
+            raise ValueError("orc_gm_play(%d,%d,%d) -> %d" % (colour, row, col, r))
+
+    def replay(self, moves):
+        for m in moves:
+            colour, row, col = decode_move(int(m))
+            if row is not None:
+                self.play(colour, row, col)
+        return self
+
+    @property
+    def step(self):
+        return int(self.lib.orc_gm_step(self.h))
+
+    @step.setter
+    def step(self, v):
+        self.lib.orc_gm_set_step(self.h, int(v))
+
+    def genmove(self, colour, seed_base=20151001):
+        """returns (move or None, tables) — tables: dict of 13x13 double arrays total_mark, mc, amaf1, amaf2"""
+        row, col = C.c_int(-1), C.c_int(-1)
+        t = {k: np.zeros((13, 13)) for k in ("total_mark", "mc", "amaf1", "amaf2")}
+        dp = C.POINTER(C.c_double)
+        moved = self.lib.orc_gm_genmove(self.h, colour, seed_base, C.byref(row), C.byref(col),
+                                        *[t[k].ctypes.data_as(dp) for k in ("total_mark", "mc", "amaf1", "amaf2")])
+        return ((row.value, col.value) if moved else None), t
+
+    def static_mark(self, colour, row, col):
+        """total_mark[row][col] - mc[row][col] after MyWorker::work at avrg_win = 0: the static
+        pattern marks of AgentGo.cpp:104-282 (an integer combination of bonus_a, bonus_b)."""
+        return float(self.lib.orc_gm_static_mark(self.h, colour, row, col, 1))
