@@ -149,20 +149,29 @@ struct WarpBoard {
     // transition is linear over GF(2), so T^16 is applied as a per-lane nibble-table lookup
     // (LDG.128) folded by four redux.xor, and then every lane generates its own 16 draws.
     __device__ __forceinline__ void refill(const RngParams& prm, const JumpTable* __restrict__ jt) {
-        TinyMT mine;
-        mine.s0 = g0; mine.s1 = g1; mine.s2 = g2; mine.s3 = g3;
         const bool lo16 = lane < 16, lo8 = (lane & 8) == 0;
         const uint32_t sh = (lane & 7) * 4;
         const uint4* __restrict__ row = &jt->e[lane * 16];
-#pragma unroll 1
+        // The half of the ring about to be written is free (at most kLookahead draws are pending
+        // and they sit in the other half), so the segment-start states are parked there: state l
+        // in the first 16 bytes of lane l's own 32-byte segment, which that lane reads back before
+        // it writes its draws over it.  (A register capture costs a compare and four selects per
+        // step in all lanes; this is one store.)
+        uint4* park = reinterpret_cast<uint4*>(ring.p + (gen_end & (kRing - 1)));
+#pragma unroll 4
         for (int l = 0; l < 32; l++) {
-            if (lane == l) { mine.s0 = g0; mine.s1 = g1; mine.s2 = g2; mine.s3 = g3; }
+            park[2 * l] = make_uint4(g0, g1, g2, g3);
             const uint32_t word = lo16 ? (lo8 ? g0 : g1) : (lo8 ? g2 : g3);
             const uint4 t = __ldg(&row[(word >> sh) & 15u]);
             g0 = __reduce_xor_sync(kFull, t.x);
             g1 = __reduce_xor_sync(kFull, t.y);
             g2 = __reduce_xor_sync(kFull, t.z);
             g3 = __reduce_xor_sync(kFull, t.w);
+        }
+        TinyMT mine;
+        {
+            const uint4 st = park[2 * lane];
+            mine.s0 = st.x; mine.s1 = st.y; mine.s2 = st.z; mine.s3 = st.w;
         }
         const uint32_t base = gen_end + (uint32_t)lane * kSeg;
 #pragma unroll 2
