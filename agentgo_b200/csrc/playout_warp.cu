@@ -81,7 +81,8 @@ __device__ __forceinline__ int fBh(uint32_t hi) { return (int)(hi & 511u); }    
 __device__ __forceinline__ int fCol(uint32_t w) { return (int)(w >> 30); }
 __device__ __forceinline__ bool isEmpty(uint32_t w) { return w < 0x40000000u; }
 __device__ __forceinline__ bool isBorder(uint32_t w) { return w >= 0xc0000000u; }
-__device__ __forceinline__ bool is_stone(int col) { return ((col + 1) & 2) != 0; }   // 1 or 2
+// colour 1 or 2: adding a quarter turn moves exactly those two into the upper half of the range
+__device__ __forceinline__ bool isStone(uint32_t w) { return (int32_t)(w + 0x40000000u) < 0; }
 __device__ __forceinline__ uint32_t pack0(int a, int b, int col) {
     return (uint32_t)a | ((uint32_t)b << 16) | ((uint32_t)col << 30);
 }
@@ -196,6 +197,7 @@ struct WarpBoard {
     //   kEvalReserve complex mode: `reserve` only (additionally no friend sum)
     struct Eval {
         bool empty, kill, survive, chase, bad, reserve;
+        bool live;      // kEvalAll only, warp-uniform: false = the early exit was taken, all masks are empty
     };
     enum { kEvalAll = 0, kEvalBad = 1, kEvalReserve = 2 };
     template <int MODE>
@@ -219,7 +221,7 @@ struct WarpBoard {
                 return z;
             }
         }
-        const bool nb_stone = is_stone(ncol);
+        const bool nb_stone = isStone(wn);
         const int root = nb_stone ? fA(wn) : -1 - (lane & 3);       // distinct negatives per direction
         const int hp = (int)(w1[nb_stone ? root : 0] & 0xffffu);
 
@@ -237,7 +239,7 @@ struct WarpBoard {
             // the neighbourhood phase are empty and nothing else matters (~70 % of the calls)
             if (__ballot_sync(kFull, isEmpty(wc) && nb_stone && left <= 1) == 0) {
                 Eval z;
-                z.empty = z.kill = z.survive = z.chase = z.bad = z.reserve = false;
+                z.empty = z.kill = z.survive = z.chase = z.bad = z.reserve = z.live = false;
                 return z;
             }
         }
@@ -280,6 +282,7 @@ struct WarpBoard {
         e.chase = chase;
         e.reserve = eye || suicide || ko;
         e.bad = e.reserve || dying;
+        e.live = true;
         return e;
     }
 
@@ -368,10 +371,13 @@ struct WarpBoard {
             const int lm = agent == 1 ? last1 : last0;              // opponent's last move
             if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
                 const Eval f = eval_cells<kEvalAll>(agent, lm + off_cell);
-                const bool ok = f.empty && !f.bad;
-                const unsigned K = __ballot_sync(kFull, ok && f.kill);
-                const unsigned S = __ballot_sync(kFull, ok && f.survive);
-                const unsigned C = __ballot_sync(kFull, ok && f.chase);
+                unsigned K = 0, S = 0, C = 0;
+                if (f.live) {
+                    const bool ok = f.empty && !f.bad;
+                    K = __ballot_sync(kFull, ok && f.kill);
+                    S = __ballot_sync(kFull, ok && f.survive);
+                    C = __ballot_sync(kFull, ok && f.chase);
+                }
                 if ((K | S | C) != 0) {
                     // lane k = iteration k of `for (k = 0; k < 9; k++)`
                     const uint32_t a = mod_small<3>(peek(2 * lane));
@@ -464,7 +470,7 @@ struct WarpBoard {
         const int nb_l = idx + off_nb;
         const uint32_t v_l = w0[nb_l];
         const int col_l = fCol(v_l);
-        const bool st_l = is_stone(col_l);
+        const bool st_l = isStone(v_l);
         const int root_l = st_l ? fA(v_l) : -1 - dl;
         const uint32_t h_l = w1[st_l ? root_l : 0];
         const unsigned same = __match_any_sync(kFull, root_l) & nib;    // directions seeing the same string
