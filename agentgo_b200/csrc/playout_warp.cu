@@ -109,7 +109,10 @@ struct WarpBoard {
                          //       zeroed ones (put maintains it); -1: stale entries are validated lazily
     int stones;          // num_black + num_white (only the sum is ever read on this path)
     int ko_key;          // exist_compete ? compete colour<<16 | idx : -1
-    int last0, last1;    // last_move[colour-1] as idx, -1 = none
+    int prev;            // last_move[] of the side that is NOT to move, as idx, -1 = none.  The two sides
+                         // alternate strictly, so after the first move of a playout this is simply the
+                         // previous move (or -1 after a pass, Board.cpp:200-203): one register
+                         // instead of the reference's pair indexed by colour.
     int ending;          // game_ending
     // --- random numbers: a ring of pre-generated rand() values (see refill) ---
     SmemArr<uint16_t> ring;      // kRing entries, entry (p & (kRing-1)) holds draw number p of this playout
@@ -368,7 +371,7 @@ struct WarpBoard {
         }
         if (!complex_mode) {
             n_dead = -1;                                            // put stops maintaining elist
-            const int lm = agent == 1 ? last1 : last0;              // opponent's last move
+            const int lm = prev;                                    // opponent's last move
             if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
                 const Eval f = eval_cells<kEvalAll>(agent, lm + off_cell);
                 unsigned K = 0, S = 0, C = 0;
@@ -578,7 +581,6 @@ struct WarpBoard {
             if (victim >= 0) kill_string(victim);
         }
         }
-        if (agent == 1) last0 = idx; else last1 = idx;             // :171
     }
 
     // Board::countScore(agent) - countScore(enemy), Board.cpp:910-925, strided over the lanes:
@@ -665,8 +667,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         bd.n_el = pos.n_el;
         bd.stones = pos.stones;
         bd.ko_key = pos.ko_key_col > 0 ? ((pos.ko_key_col << 16) | pos.ko_idx) : -1;
-        bd.last0 = pos.last[0];
-        bd.last1 = pos.last[1];
+        bd.prev = pos.last[2 - d.first];                            // last_move[enemy of the first mover]
         bd.ending = pos.ending;
         bd.pos = 0;
         bd.gen_end = 0;
@@ -691,13 +692,13 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
 
         // pair loop of MyWorker::work (AgentGo.cpp:295-325) / testAvrgWin (:422-443), one move
         // per iteration: the loop ends after a pair in which neither side moved.
-        const int first = d.first;
+        int colour = d.first;
+        bool second = false;            // this move closes its pair
         bool first_moved = true, fault = false;
         uint32_t mv = 0;
-        int n_log = 0;
+        int n_log = 0, cstep = 2;       // cstep is 2 in the first pair (:293,:297)
 #pragma unroll 1
-        for (int t = 0;; t++) {
-            const int colour = (t & 1) ? 3 - first : first;
+        for (;;) {
             while (bd.gen_end - bd.pos < (uint32_t)WB::kLookahead) bd.refill(a.rng, a.jump);
             const int r = bd.random_piece(colour);
             if (r >= 0) {
@@ -705,8 +706,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
                 mv++;
                 if (AMAF) {
                     // mark[r] / mark2[r] = cstep of the FIRST play of that side at r (:304,:319);
-                    // cstep is 2 in the first pair (:293,:297); only cstep <= AMAF_RANGE is ever used
-                    const int cstep = 2 + (t >> 1);
+                    // only cstep <= AMAF_RANGE is ever used
                     if (cstep <= kAmafRange) {
                         const uint32_t key = (uint32_t)r | (colour == d.agent ? 512u : 0u);
                         bool dup = false;
@@ -719,11 +719,17 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
                 }
             } else {                                                // Board::pass, Board.cpp:200-203
                 bd.ko_key = -1;
-                if (colour == 1) bd.last0 = -1; else bd.last1 = -1;
             }
-            if (!(t & 1)) first_moved = r >= 0;
-            else if (!first_moved && r < 0) break;
-            if ((int)mv > a.max_moves) { fault = true; break; }
+            bd.prev = r;                                            // Board.cpp:171 / :202
+            if (second) {
+                if (!first_moved && r < 0) break;
+                if ((int)mv > a.max_moves) { fault = true; break; } // fault detector, once per pair
+                if (AMAF) cstep++;
+            } else {
+                first_moved = r >= 0;
+            }
+            second = !second;
+            colour = 3 - colour;
         }
         __syncwarp();
         const int diff = fault ? -32768 : bd.score_diff(d.agent);
