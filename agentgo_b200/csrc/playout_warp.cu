@@ -206,8 +206,10 @@ struct WarpBoard {
     template <int MODE>
     __device__ __forceinline__ Eval eval_cells(int agent, int cidx) const {
         const unsigned nib = 15u << (lane & ~3);                    // this cell's four lanes
-        const uint32_t wc = w0[cidx];
-        const bool cell_on = !isBorder(wc);
+        // kEvalBad is only ever handed points of the board (candidates of the rejection phase; cbuf
+        // starts out holding one), so it neither loads the cell nor guards the neighbour offsets
+        const uint32_t wc = MODE == kEvalBad ? 0u : w0[cidx];
+        const bool cell_on = MODE == kEvalBad || !isBorder(wc);
         const uint32_t wn = w0[cell_on ? cidx + off_nb : 0];        // w0[0] is a border cell
         const int ncol = fCol(wn);
         if (MODE == kEvalBad) {
@@ -417,7 +419,7 @@ struct WarpBoard {
                     __syncwarp();
                     const int ncand = min(8, __popc(cand));
                     const int cell = lane >> 2;
-                    const uint32_t entry = cell < ncand ? cbuf[cell] : 0u;        // 0 = a border cell
+                    const uint32_t entry = cbuf[cell];          // cells >= ncand: a stale or the initial point, unused
                     const Eval e = eval_cells<kEvalBad>(agent, (int)(entry & 511u));
                     const unsigned good = __ballot_sync(kFull, cell < ncand && !e.bad);
                     if (good) {
@@ -466,6 +468,7 @@ struct WarpBoard {
         if (n_dead >= 0) {
             elist[h0[2 * idx]] = 0;
             n_dead++;
+            __syncwarp();       // (also keeps this rare block a branch instead of five predicated instructions)
         }
         // lane d (mod 4) looks at neighbour d (up, left, down, right): colour, string, liberties
         const int dl = lane & 3;
@@ -669,6 +672,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         bd.ko_key = pos.ko_key_col > 0 ? ((pos.ko_key_col << 16) | pos.ko_idx) : -1;
         bd.prev = pos.last[2 - d.first];                            // last_move[enemy of the first mover]
         bd.ending = pos.ending;
+        if (lane < 8) bd.cbuf[lane] = (uint16_t)(WB::W + 1);        // any point of the board (see eval_cells)
         bd.pos = 0;
         bd.gen_end = 0;
         bd.n_dead = -1;
