@@ -502,6 +502,14 @@ struct WarpBoard {
             if (fr_mask == 0) {
                 w0[idx] = pack0(idx, kNilP, agent);                 // SetNode::init, SetNode.cpp:31-44
                 w1[idx] = (uint32_t)hp_self | ((uint32_t)idx << 16);
+            } else if ((fr_mask & (fr_mask - 1u)) == 0) {
+                // one own string (most merges): the new stone is appended to it, nothing is relabelled
+                const int top = 31 - __clz(fr_mask);
+                const int fk = __shfl_sync(kFull, root_l, top);
+                const int tail = (int)(__shfl_sync(kFull, h_l, top) >> 16);
+                h0[2 * tail + 1] = packHi(idx, agent);
+                w0[idx] = pack0(fk, kNilP, agent);
+                w1[fk] = (uint32_t)hp_total | ((uint32_t)idx << 16);
             } else {
                 const int fk = __shfl_sync(kFull, root_l, 31 - __clz(fr_mask));
                 // lane of F_i links its tail to the head of F_(i-1), the lane of F_1 to the new stone
@@ -514,8 +522,8 @@ struct WarpBoard {
                 w0[idx] = pack0(fk, kNilP, agent);
                 w1[fk] = (uint32_t)hp_total | ((uint32_t)idx << 16);
                 // strings F_1..F_(k-1) are relabelled to Fk (:284-289)
-                const unsigned others = fr_mask & (fr_mask - 1u) ? fr_mask & ~(1u << (31 - __clz(fr_mask))) : 0u;
-                if (others && !(others & (others - 1u))) {
+                const unsigned others = fr_mask & ~(1u << (31 - __clz(fr_mask)));
+                if (!(others & (others - 1u))) {
                     // the usual case of a merge: one string, walked warp-uniformly
                     const int d1 = __ffs(others) - 1;
                     const int t1 = (int)(__shfl_sync(kFull, h_l, d1) >> 16);
@@ -525,7 +533,7 @@ struct WarpBoard {
                         if (sidx == t1) break;
                         sidx = fBh(h0[2 * sidx + 1]);
                     }
-                } else if (others) {
+                } else {
                     // two or three strings: each is walked by its own lane
                     bool walk = own_l && root_l != fk;
                     int sidx = root_l;
