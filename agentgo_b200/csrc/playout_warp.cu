@@ -63,12 +63,18 @@ struct SmemArr {
         if ((unsigned)i >= (unsigned)n) { atomicAdd(&g_bounds_violations, 1ull); i = 0; }
         return p[i];
     }
+    // pointer to elements i, i+1 (both checked)
+    __device__ __forceinline__ T* pair(int i) const {
+        if ((unsigned)i + 1u >= (unsigned)n) { atomicAdd(&g_bounds_violations, 1ull); i = 0; }
+        return p + i;
+    }
 };
 #else
 template <typename T>
 struct SmemArr {
     T* p;
     __device__ __forceinline__ T& operator[](int i) const { return p[i]; }
+    __device__ __forceinline__ T* pair(int i) const { return p + i; }
 };
 #endif
 
@@ -325,7 +331,7 @@ struct WarpBoard {
         if (spaces == 0) return -1;
         // Complex mode is sticky (game_ending, :348-351): the array is made dense once and then
         // kept current by put (zeroes the entry) and kill_string (appends).
-        if (n_dead < 0 || 4 * n_dead > n_el) { n_dead = 0; compact(); }
+        if (n_dead < 0 || n_dead >= 8) { n_dead = 0; compact(); }      // 8 dead entries = one wasted round below
         int reserved_total = 0;
 #pragma unroll 1
         for (int base = 0; base < n_el; base += 8) {
@@ -404,11 +410,11 @@ struct WarpBoard {
 #pragma unroll 1
             for (int count = 0; count < kEndingThreshold;) {
                 const int B = min(32, kEndingThreshold - count);
+                const int A = min(32, kEndingThreshold - 1 - count);    // the 100th draw is never accepted (:402-405)
                 const uint32_t row = mod_small<N>(peek(2 * lane));
                 const uint32_t cl = mod_small<N>(peek(2 * lane + 1));
                 const int idx = (int)(row * W + cl + (W + 1));
-                // the 100th draw is never accepted (:402-405)
-                const bool can = lane < B && count + lane + 1 != kEndingThreshold && isEmpty(w0[idx]);
+                const bool can = lane < A && isEmpty(w0[idx]);
                 unsigned cand = __ballot_sync(kFull, can);
                 // evaluate the empty candidates in draw order, 8 per round
 #pragma unroll 1
@@ -529,9 +535,10 @@ struct WarpBoard {
                     const int t1 = (int)(__shfl_sync(kFull, h_l, d1) >> 16);
 #pragma unroll 1
                     for (int sidx = __shfl_sync(kFull, root_l, d1);;) {
-                        h0[2 * sidx] = (uint16_t)fk;
+                        uint16_t* c = h0.pair(2 * sidx);            // one address for both halves
+                        c[0] = (uint16_t)fk;
                         if (sidx == t1) break;
-                        sidx = fBh(h0[2 * sidx + 1]);
+                        sidx = fBh(c[1]);
                     }
                 } else {
                     // two or three strings: each is walked by its own lane
@@ -578,8 +585,9 @@ struct WarpBoard {
                         h0[2 * t1 + 1] = packHi(s2, agent);
 #pragma unroll 1
                         for (int k = s2; k != kNilP;) {
-                            h0[2 * k] = (uint16_t)sn;
-                            k = fBh(h0[2 * k + 1]);
+                            uint16_t* c = h0.pair(2 * k);
+                            c[0] = (uint16_t)sn;
+                            k = fBh(c[1]);
                         }
                     }
                 }
