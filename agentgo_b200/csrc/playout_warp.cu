@@ -121,12 +121,15 @@ struct WarpBoard {
                          // instead of the reference's pair indexed by colour.
     int ending;          // game_ending
     // --- random numbers: a ring of pre-generated rand() values (see refill) ---
-    SmemArr<uint16_t> ring;      // kRing entries, entry (p & (kRing-1)) holds draw number p of this playout
+    SmemArr<uint16_t> ring;      // kRing entries, entry (p & (kRing-1)) holds draw number p of this playout;
+                                 // then kMirror more that repeat the first kMirror, so that a read of
+                                 // up to kMirror draws ahead of pos needs no wrap-around per lane
     uint32_t g0, g1, g2, g3;     // generator state at draw number gen_end (warp-uniform)
     uint32_t pos;                // next draw to be consumed = rand() calls made so far
     uint32_t gen_end;            // draws [pos, gen_end) are in the ring
 
     static constexpr int kRing = 1024;
+    static constexpr int kMirror = 64;              // peek(i) is used with i < 64
     static constexpr int kSeg = 16;                 // draws generated per lane per refill
     static constexpr int kRefill = 32 * kSeg;       // 512 draws per refill
     // One move consumes at most 18 (neighbourhood) + 200 (rejection) + 1 (complex) draws and the
@@ -144,7 +147,7 @@ struct WarpBoard {
     }
 
     // rand() number pos + i (i < kLookahead), without consuming it
-    __device__ __forceinline__ uint32_t peek(uint32_t i) const { return ring[(pos + i) & (kRing - 1)]; }
+    __device__ __forceinline__ uint32_t peek(uint32_t i) const { return ring[(pos & (kRing - 1)) + i]; }
     // v % M for a 15-bit value and a small constant M: one IMAD.HI and one IMAD
     // (q = floor(v * ceil(2^32 / M) / 2^32) is exact for v < 2^15)
     template <uint32_t M>
@@ -183,11 +186,14 @@ struct WarpBoard {
             const uint4 st = park[2 * lane];
             mine.s0 = st.x; mine.s1 = st.y; mine.s2 = st.z; mine.s3 = st.w;
         }
-        const uint32_t base = gen_end + (uint32_t)lane * kSeg;
+        const uint32_t base = (gen_end + (uint32_t)lane * kSeg) & (kRing - 1);   // segments do not wrap
+        const bool mirrored = base < kMirror;
 #pragma unroll 2
         for (int j = 0; j < kSeg; j++) {
             mine.next_state(prm.mat1, prm.mat2);
-            ring[(base + j) & (kRing - 1)] = (uint16_t)(mine.temper(prm.tmat) >> 17);
+            const uint16_t v = (uint16_t)(mine.temper(prm.tmat) >> 17);
+            ring[base + j] = v;
+            if (mirrored) ring[kRing + base + j] = v;
         }
         gen_end += kRefill;
         __syncwarp();
@@ -629,7 +635,7 @@ template <int N>
 struct BoardWords {
     static constexpr int NP = (N + 2) * (N + 2);
     static constexpr int board = ((2 * NP + kElistCap / 2 + 4 + 31) / 32) * 32;
-    static constexpr int value = board + WarpBoard<N>::kRing / 2;
+    static constexpr int value = board + (WarpBoard<N>::kRing + WarpBoard<N>::kMirror) / 2;
     static constexpr int kAmafLog = 80;                     // first plays with cstep <= 40: at most 78
     static constexpr int value_amaf = value + kAmafLog / 2;
 };
@@ -653,7 +659,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
     bd.cbuf.p = bd.elist.p + kElistCap;
     bd.ring.p = reinterpret_cast<uint16_t*>(base + BoardWords<N>::board);
 #ifdef AGB_CHECK_BOUNDS
-    bd.w0.n = WB::NP; bd.w1.n = WB::NP; bd.h0.n = 2 * WB::NP; bd.elist.n = kElistCap; bd.cbuf.n = 8; bd.ring.n = WB::kRing;
+    bd.w0.n = WB::NP; bd.w1.n = WB::NP; bd.h0.n = 2 * WB::NP; bd.elist.n = kElistCap; bd.cbuf.n = 8; bd.ring.n = WB::kRing + WB::kMirror;
 #endif
     bd.init_lane(lane);
 
