@@ -272,7 +272,7 @@ def run_b200(args):
         rates, info = cpu_reference(sample_seconds=args.cpu_seconds)
         cpu = {"value": rates[0][0], "unit": UNIT, "cores": info["cores"], "threads": info["threads"],
                "kind": info["kind"], "sample": info["sample"], "seconds": rates[0][1]}
-    pos_bytes = 2 * 441 * 4 + 16 + 16          # PaddedPosition + StartDesc
+    pos_bytes = (2 * 441 + 181) * 4 + 16 + 20  # PaddedPosition (w0, w1, elist, scalars) + StartDesc
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": workload(args.playouts, world),
