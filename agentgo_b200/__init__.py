@@ -32,7 +32,7 @@ SYMBOLS = [
     "agb_playouts_amaf", "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
     "agb_set_allreduce", "agb_playouts_batch", "agb_genmove", "agb_measure_peaks",
     "agb_debug_violations", "agb_attach_nccl", "agb_detach_nccl", "agb_static_units", "agb_last_marks",
-    "agb_genmove_step", "agb_set_genmove_step",
+    "agb_genmove_step", "agb_set_genmove_step", "agb_calc_result", "agb_random_piece",
 ]
 
 
@@ -117,6 +117,8 @@ def lib():
     l.agb_genmove.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64,
                               C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                               C.POINTER(Stats)]
+    l.agb_random_piece.argtypes = [vp, C.c_int, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    l.agb_calc_result.argtypes = [vp, C.POINTER(C.c_int)]
     l.agb_static_units.argtypes = [vp, C.c_int, C.c_int, C.c_int, i64p, i64p]
     l.agb_last_marks.argtypes = [vp, C.POINTER(C.c_double), C.c_int]
     l.agb_genmove_step.argtypes = [vp]
@@ -318,6 +320,18 @@ class Engine:
         self._chk(self._l.agb_genmove(self._h, colour, P_per_candidate, P_root, seed_base,
                                       C.byref(row), C.byref(col), C.byref(is_pass), C.byref(st)))
         return (None if is_pass.value else (row.value, col.value)), st.as_dict()
+
+    def random_piece(self, colour, seed):
+        """Board::getRandomPiece on the host (the match referee's fallback move); (row, col) or None."""
+        row, col, is_pass = C.c_int(), C.c_int(), C.c_int()
+        self._chk(self._l.agb_random_piece(self._h, colour, seed, C.byref(row), C.byref(col), C.byref(is_pass)))
+        return None if is_pass.value else (row.value, col.value)
+
+    def calc_result(self):
+        """CalcResults of the reference's match harness (GeneHatchery.cpp:393-436): black - white."""
+        d = C.c_int()
+        self._chk(self._l.agb_calc_result(self._h, C.byref(d)))
+        return d.value
 
     def static_units(self, colour, row, col):
         """-> (units_a, units_b): the static pattern marks of MyWorker::work (AgentGo.cpp:104-282)

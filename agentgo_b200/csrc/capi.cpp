@@ -187,6 +187,25 @@ int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
     AGB_GUARD_END(h)
 }
 
+int agb_calc_result(const agb_engine* h, int* black_minus_white) {
+    if (!h || !black_minus_white) return AGB_ERR_INVALID;
+    *black_minus_white = h->e->board.calc_result();
+    return AGB_OK;
+}
+
+int agb_random_piece(agb_engine* h, int colour, uint32_t seed, int* row, int* col, int* is_pass) {
+    if (!h || !row || !col || !is_pass) return AGB_ERR_INVALID;
+    if (colour != AGB_BLACK && colour != AGB_WHITE) return h->e->fail(AGB_ERR_INVALID, "bad colour");
+    const agb_config& c = h->e->cfg;
+    agb::RngParams prm = {c.mat1 ? c.mat1 : AGB_TINYMT_MAT1, c.mat2 ? c.mat2 : AGB_TINYMT_MAT2, c.tmat ? c.tmat : AGB_TINYMT_TMAT};
+    const int idx = h->e->board.random_piece(colour, seed, prm);
+    const int n = h->e->board.n();
+    *is_pass = idx < 0;
+    *row = idx < 0 ? -1 : idx / n;
+    *col = idx < 0 ? -1 : idx % n;
+    return AGB_OK;
+}
+
 int agb_static_units(const agb_engine* h, int colour, int row, int col, int64_t* units_a, int64_t* units_b) {
     if (!h || !units_a || !units_b) return AGB_ERR_INVALID;
     const int n = h->e->board.n();

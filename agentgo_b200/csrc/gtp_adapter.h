@@ -50,6 +50,7 @@ public:
         last.device_ms = 0; last.playouts = 0;
     }
     agb_stats last;       // statistics of the last genmove
+    void SetSeed(unsigned long long s) { seed = s; }   // the reference reseeds per process (srand(time(0)), AgentGo.cpp:724)
     // further engines of a multi-GPU group (agb_attach_nccl): they mirror every board change and
     // run the same genmove concurrently, one host thread each
     std::vector<agb_engine*> peers;

@@ -5,6 +5,7 @@
 //               [--device D] [--gpus N] [--seed S] [--kernel auto|thread|warp]
 //               [--amaf] [--static] [--book] [--reference-policy]
 //               [--selfplay [--max-moves K]]
+//               [--match G [--white-playouts P] [--white-policy flat|reference]]
 //
 //   --playouts P        playouts per candidate (reference: numset = 150, AgentGo.cpp:85)
 //   --total-playouts M  fixed budget per genmove, split evenly over the candidates
@@ -15,6 +16,12 @@
 //   --static            add the static pattern marks of MyWorker::work (AgentGo.cpp:104-282)
 //   --book              answer the first four genmoves from the 13x13 opening book (AgentGo.cpp:468-572)
 //   --reference-policy  all three: the complete MyGame::onMove of the reference
+//   --match G           G games between two configurations of this engine under the referee of the
+//                       reference's GA tuner (SimulateOneGame, GeneHatchery.cpp:438-568): black is the
+//                       engine configured by the options above, white the one given by --white-*;
+//                       the referee keeps its own board, gives a side that passes a random policy
+//                       move instead (getRandomPiece, :474,:520), ends the game when a side has no
+//                       move after the other had none either, and scores with CalcResults (:393-436)
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -33,7 +40,8 @@ int main(int argc, char** argv) {
     long long P = 150, R = 500, total = 0;
     unsigned long long seed = 20151001ull;
     bool selfplay = false;
-    int max_moves = 800, gpus = 1;
+    int max_moves = 800, gpus = 1, match_games = 0, white_policy = -1;
+    long long white_P = -1;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto next = [&](const char* name) -> const char* {
@@ -53,6 +61,9 @@ int main(int argc, char** argv) {
         else if (a == "--book") cfg.genmove_book = 1;
         else if (a == "--reference-policy") cfg.genmove_amaf = cfg.genmove_static = cfg.genmove_book = 1;
         else if (a == "--gpus") gpus = atoi(next("--gpus"));
+        else if (a == "--match") match_games = atoi(next("--match"));
+        else if (a == "--white-playouts") white_P = atoll(next("--white-playouts"));
+        else if (a == "--white-policy") white_policy = std::string(next("--white-policy")) == "reference" ? 1 : 0;
         else if (a == "--kernel") {
             const std::string k = next("--kernel");
             cfg.kernel = k == "thread" ? AGB_KERNEL_THREAD : (k == "warp" ? AGB_KERNEL_WARP : AGB_KERNEL_AUTO);
@@ -77,6 +88,86 @@ int main(int argc, char** argv) {
         return 1;
     }
     agb_engine* eng = engines[0];
+    if (match_games > 0) {
+        // white: same device and board size, its own playout count and policy
+        agb_config wc = cfg;
+        if (white_policy >= 0) wc.genmove_amaf = wc.genmove_static = wc.genmove_book = white_policy;
+        agb_config rc = cfg;
+        rc.device = -1;                                    // the referee only keeps a board
+        agb_engine *weng = nullptr, *ref = nullptr;
+        if (agb_create(&wc, &weng) != AGB_OK || agb_create(&rc, &ref) != AGB_OK) {
+            fprintf(stderr, "agb_create failed: %s\n", agb_last_error(nullptr));
+            return 1;
+        }
+        MyGame side[2] = {MyGame(eng, total > 0 ? -total : P, R, seed),
+                          MyGame(weng, white_P > 0 ? white_P : P, R, seed + 0x9e3779b9ull)};
+        const char cname[2] = {'b', 'w'};
+        auto tell = [&](int who, const std::string& cmd) {
+            std::ostringstream reply;
+            side[who].HandleLine(cmd, reply);
+            return reply.str();
+        };
+        auto vertex = [&](int row, int col) {
+            return std::string(1, GaIntToChar(row)) + std::to_string(col + 1);
+        };
+        std::vector<int> dscores;
+        int black_wins = 0;
+        long long stones = 0;
+        for (int g = 0; g < match_games; g++) {
+            for (int w = 0; w < 2; w++) {
+                tell(w, "boardsize " + std::to_string(cfg.board_size));
+                tell(w, "clear_board");
+            }
+            agb_clear_board(ref);
+            // a new process per game in the reference: a new seed per game here
+            side[0].SetSeed(seed + 1000003ull * (unsigned long long)g);
+            side[1].SetSeed(seed + 0x9e3779b9ull + 1000003ull * (unsigned long long)g);
+            // played[c]: did side c put a stone in its last turn (bplay / lastwplay, :461,:511)
+            bool played[2] = {true, true};
+            int dscore = 0;
+            for (int t = 0; t < 2 * max_moves; t++) {
+                const int c = t & 1, o = 1 - c;
+                const std::string rep = tell(c, std::string("genmove ") + cname[c]);
+                int row = -1, col = -1;
+                bool moved = rep.size() > 3 && rep.compare(2, 4, "pass") != 0 && rep[0] == '=';
+                if (moved) {                                            // "= D4": letter = row, number-1 = col
+                    row = GaCharToInt(tolower((int)rep[2]));
+                    col = atoi(rep.c_str() + 3) - 1;
+                    agb_play(ref, c + 1, row, col);
+                    tell(o, std::string("play ") + cname[c] + " " + vertex(row, col));
+                } else {
+                    int is_pass = 1;
+                    agb_random_piece(ref, c + 1, (uint32_t)(seed + 977ull * (unsigned long long)g + (unsigned long long)t), &row, &col, &is_pass);
+                    if (is_pass) {
+                        if (!played[o]) { agb_calc_result(ref, &dscore); break; }   // :476-481,:522-527
+                        agb_pass(ref, c + 1);
+                        tell(o, std::string("play ") + cname[c] + " pass");
+                    } else {
+                        tell(c, std::string("play ") + cname[c] + " " + vertex(row, col));
+                        tell(o, std::string("play ") + cname[c] + " " + vertex(row, col));
+                        agb_play(ref, c + 1, row, col);
+                        moved = true;
+                    }
+                }
+                played[c] = moved;
+                if (moved) stones++;
+                if (t == 2 * max_moves - 1) agb_calc_result(ref, &dscore);
+            }
+            dscores.push_back(dscore);
+            if (dscore > 0) black_wins++;
+            fprintf(stderr, "game %d: black - white = %d\n", g + 1, dscore);
+        }
+        printf("{\"match\": {\"games\": %d, \"board_size\": %d, \"black_playouts\": %lld, \"white_playouts\": %lld, "
+               "\"black_policy\": \"%s\", \"white_policy\": \"%s\", \"black_wins\": %d, \"stones_played\": %lld, \"dscore\": [",
+               match_games, cfg.board_size, P, white_P > 0 ? white_P : P, cfg.genmove_static ? "reference" : "flat",
+               wc.genmove_static ? "reference" : "flat", black_wins, stones);
+        for (size_t i = 0; i < dscores.size(); i++) printf("%s%d", i ? ", " : "", dscores[i]);
+        printf("]}}\n");
+        agb_destroy(weng);
+        agb_destroy(ref);
+        for (agb_engine* e : engines) agb_destroy(e);
+        return 0;
+    }
     MyGame gm(eng, total > 0 ? -total : P, R, seed);
     gm.peers.assign(engines.begin() + 1, engines.end());
     int rc = 0;

@@ -123,6 +123,38 @@ int HostBoard::check(int which, int colour, int row, int col) const {
 
 int HostBoard::count_score(int colour) const { return open().count_score(colour); }
 
+// CalcResults, GeneHatchery.cpp:393-436.  SET_SCORE (:379-390) `continue`s the column loop at the
+// first neighbour that is a stone, in the order up, down, left, right; the sweep is in place.
+int HostBoard::calc_result() const {
+    const int n = pos_.n;
+    int data[kMaxNN];
+    for (int idx = 0; idx < n * n; idx++) data[idx] = (int)((pos_.w0[idx] >> 20) & 3u);
+    bool changed = true;
+    while (changed) {
+        changed = false;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                if (data[i * n + j] != 0) continue;
+                const int nb[4] = {i > 0 ? data[(i - 1) * n + j] : 0, i < n - 1 ? data[(i + 1) * n + j] : 0,
+                                   j > 0 ? data[i * n + j - 1] : 0, j < n - 1 ? data[i * n + j + 1] : 0};
+                for (int d = 0; d < 4; d++)
+                    if (nb[d] == 1 || nb[d] == 2) { data[i * n + j] = nb[d]; changed = true; break; }
+            }
+    }
+    int dscore = 0;
+    for (int idx = 0; idx < n * n; idx++) dscore += data[idx] == 1 ? 1 : -1;     // :430
+    return dscore;
+}
+
+int HostBoard::random_piece(int colour, uint32_t seed, const RngParams& prm) {
+    Ref r = open();
+    Rng rng;
+    rng.seed(seed, prm);
+    const int idx = r.random_piece(rng, colour);
+    close(r);                                   // game_ending may have been latched, Board.cpp:407
+    return idx;
+}
+
 bool HostBoard::is_candidate(int colour, int row, int col) const {
     const Ref r = open();
     const int idx = row * pos_.n + col;

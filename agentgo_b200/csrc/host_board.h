@@ -35,6 +35,10 @@ public:
     // which: 0 suicide 1 kill 2 survive 3 dying 4 chase 5 true eye 6 compete 7 no-sense
     int check(int which, int colour, int row, int col) const;
     int count_score(int colour) const;
+    // CalcResults of the reference's match harness, GeneHatchery.cpp:393-436: black - white
+    int calc_result() const;
+    // Board::getRandomPiece on this board with a TinyMT32 stream seeded by `seed`; idx or -1
+    int random_piece(int colour, uint32_t seed, const RngParams& prm);
     // the candidate filter of MyGame::onMove, AgentGo.cpp:586-592
     bool is_candidate(int colour, int row, int col) const;
     // the argmax filter of MyGame::onMove, AgentGo.cpp:651 (no checkNoSense there)

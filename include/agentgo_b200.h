@@ -21,6 +21,7 @@
  *   MyWorker::work static marks    AgentGo.cpp:104-282  agb_static_units, agb_genmove (cfg.genmove_static)
  *   Board::check*                  Board.cpp:480-755    agb_check
  *   Board::countScore              Board.cpp:910        agb_count_score
+ *   CalcResults (match scorer)     GeneHatchery.cpp:393 agb_calc_result
  *
  * Conventions
  *   - plain C, no C++ types, no exceptions across the boundary;
@@ -147,6 +148,21 @@ int agb_get_board(const agb_engine* h, uint8_t* colours /* N*N */, int* n);
  *        7 no-sense.   returns 0/1, or <0 on error.                          */
 int agb_check(const agb_engine* h, int which, int colour, int row, int col);
 int agb_count_score(const agb_engine* h, int colour);
+
+/* Final score of a finished game the way the reference's match harness counts it (CalcResults,
+ * GeneHatchery.cpp:379-436): on a copy of the board, sweep the points in row-major order; an empty
+ * point takes the colour of the first stone among its up, down, left, right neighbours (values
+ * written earlier in the same sweep count); repeat until a sweep changes nothing; then
+ * *black_minus_white = #black - #(everything else).  Host only.                              */
+int agb_calc_result(const agb_engine* h, int* black_minus_white);
+
+/* Board::getRandomPiece(colour) (Board.cpp:341-411) on the engine's board, on the HOST, drawing
+ * from a TinyMT32 stream seeded with `seed` (engine's parameter set; rand() := u32 >> 17).  This is
+ * the move the reference's match referee falls back to when an engine passes
+ * (GeneHatchery.cpp:474,520) and its commented-out "play random" mode (AgentGo.cpp:453-460).  The
+ * move is NOT played; like the reference's call it may latch the board's game_ending flag
+ * (Board.cpp:348-351,407).  *is_pass = 1 when the policy finds no move.                       */
+int agb_random_piece(agb_engine* h, int colour, uint32_t seed, int* row, int* col, int* is_pass);
 
 /* debugging / parity: dump the full compact state as int32 words;
  * returns the number of words written, or <0.                               */

@@ -51,6 +51,7 @@ stream() {
 #   6. lines 1-14 (Win32 includes, `using namespace TinyMT`) and 706-end (_tmain) are not streamed;
 #      TinyMT.h / TinyOP.h types come from ref_genmove_shim.h with a serial schedule
 #   7. `class X` -> `struct X` at line starts (the harness reads MyGame::step and calls onMove)
+#   (GeneHatchery.cpp:379-436, the scorer CalcResults of the match harness, is streamed unedited)
 #   8. one line inserted after AgentGo.cpp:288 and :419 (top of the two playout loops) that starts the
 #      injected per-playout TinyMT32 stream (the reference seeds libc rand() once per process)
 stream_genmove() {
@@ -64,6 +65,10 @@ stream_genmove() {
       | sed -e 's/^class /struct /' \
             -e 's/^\([[:space:]]*\)mj->bd->clone(bdnew);/&oracle_seed_candidate(oracle_job_index, ii);/' \
             -e 's/^\([[:space:]]*\)bdtest.clone(bd);/&oracle_seed_root(ii);/'
+    echo
+    # the match scorer of the GA tuner: SET_SCORE and CalcResults, GeneHatchery.cpp:379-436
+    echo "#line 379 \"reference:GeneHatchery.cpp\""
+    tr -d '\r' < "$ref/GeneHatchery/GeneHatchery.cpp" | iconv -f GBK -t UTF-8 -c | sed -n '379,436p'
     echo
     echo "#line 1 \"oracle/ref_harness.cpp\""
     cat "$here/ref_harness.cpp"

@@ -231,6 +231,7 @@ class RefGame:
                                            C.POINTER(C.c_int), dp, dp, dp, dp]
             lib.orc_gm_static_mark.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64]
             lib.orc_gm_static_mark.restype = C.c_double
+            lib.orc_gm_calc_result.argtypes = [C.c_void_p]
             _libs[key] = lib
         self.lib = _libs[key]
         self.h = self.lib.orc_gm_new()
@@ -271,6 +272,10 @@ class RefGame:
         moved = self.lib.orc_gm_genmove(self.h, colour, seed_base, C.byref(row), C.byref(col),
                                         *[t[k].ctypes.data_as(dp) for k in ("total_mark", "mc", "amaf1", "amaf2")])
         return ((row.value, col.value) if moved else None), t
+
+    def calc_result(self):
+        """CalcResults of the match harness (GeneHatchery.cpp:393-436): black - white."""
+        return int(self.lib.orc_gm_calc_result(self.h))
 
     def static_mark(self, colour, row, col):
         """total_mark[row][col] - mc[row][col] after MyWorker::work at avrg_win = 0: the static

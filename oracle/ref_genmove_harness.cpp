@@ -82,4 +82,11 @@ double orc_gm_static_mark(void* vg, int colour, int row, int col, uint64_t seed_
     return total_mark[row][col] - mc[row][col];
 }
 
+/* CalcResults (GeneHatchery.cpp:393-436) on a COPY of the game's board (the reference scores the
+ * referee's scratch board in place): black minus white after the iterated neighbour fill. */
+int orc_gm_calc_result(void* vg) {
+    Board copy(((MyGame*)vg)->bd);
+    return CalcResults(copy);
+}
+
 }  /* extern "C" */

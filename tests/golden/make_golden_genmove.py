@@ -5,7 +5,8 @@ oracle/_ref/liboracle_ref_genmove_13.so, serial schedule, injected per-playout T
   * static_13.npz  — the static pattern marks of MyWorker::work (AgentGo.cpp:104-282) for every
                      empty, non-suicide point of 12 positions, both colours;
   * genmove_13.npz — MyGame::onMove on 6 positions: the move and the whole total_mark table, plus
-                     the opening-book sequence of a game's first eight genmoves.
+                     the opening-book sequence of a game's first eight genmoves;
+  * calc_result_13.npz — CalcResults of the match harness (GeneHatchery.cpp:393-436) on 24 positions.
 Re-run:  python tests/golden/make_golden_genmove.py   (about a minute)
 """
 import os
@@ -44,7 +45,17 @@ def static_marks(moves):
     return out
 
 
+def calc_results():
+    ps = positions(24, [5, 40, 90, 150, 200, 260, 330, 400], 4000)
+    np.savez_compressed(os.path.join(HERE, "calc_result_13.npz"),
+                        moves=np.concatenate(ps).astype(np.uint32), lens=np.array([len(p) for p in ps]),
+                        dscore=np.array([po.RefGame().replay(p).calc_result() for p in ps]))
+
+
 def main():
+    calc_results()
+    if "--calc-only" in sys.argv:
+        return
     ps = positions(12, [6, 25, 50, 80, 110, 140], 500)
     np.savez_compressed(os.path.join(HERE, "static_13.npz"),
                         moves=np.concatenate(ps).astype(np.uint32), lens=np.array([len(p) for p in ps]),

@@ -71,3 +71,22 @@ def test_multi_gpu_selfplay_equals_single_gpu(built_lib):
         assert r.returncode == 0, r.stderr
         games.append([l for l in r.stderr.splitlines() if l[:3].strip().isdigit()])
     assert len(games[0]) == 60 and games[0] == games[1]
+
+
+@pytest.mark.gpu
+def test_match_driver_on_gpu(built_lib):
+    """Row f4 of SURVEY.md §8: two configurations under the referee of the reference's GA tuner
+    (SimulateOneGame, GeneHatchery.cpp:438-568), scored by CalcResults; deterministic for a seed."""
+    import json
+    args = ["--boardsize", "9", "--playouts", "40", "--root-playouts", "100", "--match", "2",
+            "--white-playouts", "4", "--seed", "5"]
+    runs = []
+    for _ in range(2):
+        r = subprocess.run([GTP] + args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        runs.append(json.loads(r.stdout.strip().splitlines()[-1])["match"])
+    m = runs[0]
+    assert runs[0] == runs[1]
+    assert m["games"] == 2 and len(m["dscore"]) == 2 and m["stones_played"] > 60
+    assert all(-81 <= d <= 81 and d % 2 != 0 for d in m["dscore"])      # 81 points: black - rest is odd
+    assert m["black_wins"] == sum(d > 0 for d in m["dscore"])

@@ -93,3 +93,29 @@ def test_opening_book_region_order(built_lib):
     e9 = ag.Engine(9, device=-1, genmove_book=1)
     with pytest.raises(ag.AgbError):
         e9.genmove(1)
+
+
+def test_calc_result_matches_reference(built_lib):
+    """Row f4 of SURVEY.md §8: the scorer of the reference's match harness (CalcResults,
+    GeneHatchery.cpp:393-436), against the fixture and the compiled reference."""
+    g = golden("calc_result_13.npz")
+    for moves, want in zip(split_moves(g), g["dscore"]):
+        assert host_engine(moves).calc_result() == int(want)
+    assert host_engine().calc_result() == -169          # empty board: nothing is black (:430)
+    if po.genmove_ref_available():
+        for k in range(12):
+            moves = po.OracleBoard(13, "reference").random_game(1 + k % 2, 30 + 31 * k, 8800 + k)
+            assert host_engine(moves).calc_result() == po.RefGame().replay(moves).calc_result()
+
+
+def test_random_piece_matches_oracle(built_lib, port_lib):
+    """agb_random_piece = Board::getRandomPiece on the host (the referee's fallback move,
+    GeneHatchery.cpp:474,520) against every oracle available, first move of a seeded stream."""
+    from util import oracle_kinds
+    for kind in oracle_kinds(13):
+        for k in range(40):
+            moves = po.OracleBoard(13, kind).random_game(1 + k % 2, [0, 5, 40, 90, 150, 200, 260, 300][k % 8], 6000 + k)
+            colour = 1 + (k // 8) % 2
+            m = int(po.OracleBoard(13, kind).replay(moves).random_game(colour, 1, 777 + k)[0])
+            _, r, c = po.decode_move(m)
+            assert host_engine(moves).random_piece(colour, 777 + k) == (None if r is None else (r, c)), (kind, k)
