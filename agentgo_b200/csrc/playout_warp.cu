@@ -499,12 +499,12 @@ struct WarpBoard {
         const int hp_self = __popc(__ballot_sync(kFull, col_l == 0) & 15u);   // own liberties, :123-127
         const unsigned captures = __ballot_sync(kFull, enemy_l && left_l == 0) & 15u;
         const unsigned fr_mask = __ballot_sync(kFull, frnd_l && first) & 15u;  // distinct own strings
-        int hp_total = (frnd_l && first) ? left_l : 0;
-        hp_total += __shfl_xor_sync(kFull, hp_total, 1);
-        hp_total += __shfl_xor_sync(kFull, hp_total, 2);
-        hp_total += hp_self;
 
-        if (captures == 0 && hp_total != 0) {
+        // A move of the policy is never a suicide (checkSuicide, i.e. no capture, no liberty of its
+        // own and no own string with a liberty to spare, is filtered by both sampling phases and by
+        // complex mode), so "no capture" alone selects the fast path; the slow path below would
+        // also handle a self-capture, like the reference does.
+        if (captures == 0) {
             // FAST PATH (no capture, ~88 % of the moves): everything the four sequential neighbour
             // steps of :129-167 do commutes except the unions, whose net effect is known in closed
             // form.  With F1..Fk the distinct own strings in direction order, the reference ends
@@ -518,11 +518,17 @@ struct WarpBoard {
                 // one own string (most merges): the new stone is appended to it, nothing is relabelled
                 const int top = 31 - __clz(fr_mask);
                 const int fk = __shfl_sync(kFull, root_l, top);
-                const int tail = (int)(__shfl_sync(kFull, h_l, top) >> 16);
-                h0[2 * tail + 1] = packHi(idx, agent);
+                // tail of that string and its liberties after the move (its own, less the
+                // adjacencies the stone takes, plus the stone's)
+                const uint32_t ht = __shfl_sync(kFull, (h_l & 0xffff0000u) | (uint32_t)(left_l + hp_self), top);
+                h0[2 * (int)(ht >> 16) + 1] = packHi(idx, agent);
                 w0[idx] = pack0(fk, kNilP, agent);
-                w1[fk] = (uint32_t)hp_total | ((uint32_t)idx << 16);
+                w1[fk] = (ht & 0xffffu) | ((uint32_t)idx << 16);
             } else {
+                int hp_total = (frnd_l && first) ? left_l : 0;
+                hp_total += __shfl_xor_sync(kFull, hp_total, 1);
+                hp_total += __shfl_xor_sync(kFull, hp_total, 2);
+                hp_total += hp_self;
                 const int fk = __shfl_sync(kFull, root_l, 31 - __clz(fr_mask));
                 // lane of F_i links its tail to the head of F_(i-1), the lane of F_1 to the new stone
                 const unsigned lower = fr_mask & ((1u << dl) - 1u);
