@@ -32,7 +32,7 @@ SYMBOLS = [
     "agb_playouts_amaf", "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
     "agb_set_allreduce", "agb_playouts_batch", "agb_genmove", "agb_measure_peaks",
     "agb_debug_violations", "agb_attach_nccl", "agb_detach_nccl", "agb_static_units", "agb_last_marks",
-    "agb_genmove_step", "agb_set_genmove_step", "agb_calc_result", "agb_random_piece",
+    "agb_genmove_step", "agb_set_genmove_step", "agb_calc_result", "agb_random_piece", "agb_debug_event",
 ]
 
 
@@ -126,6 +126,8 @@ def lib():
     l.agb_measure_peaks.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_double), C.POINTER(C.c_int)]
     l.agb_debug_violations.restype = C.c_longlong
+    l.agb_debug_event.restype = C.c_longlong
+    l.agb_debug_event.argtypes = [C.c_int]
     _lib = l
     return l
 
@@ -133,6 +135,11 @@ def lib():
 def debug_violations():
     """Bounds violations counted by the AGB_CHECK_BOUNDS build (0 in the release build)."""
     return int(lib().agb_debug_violations())
+
+
+def debug_event(which):
+    """Coverage counters of the AGB_CHECK_BOUNDS build (see include/agentgo_b200.h)."""
+    return int(lib().agb_debug_event(which))
 
 
 def measure_peaks(device=0):

@@ -242,5 +242,6 @@ int agb_genmove(agb_engine* h, int colour, int64_t P_per_candidate, int64_t P_ro
 }
 
 long long agb_debug_violations(void) { return (long long)agb::debug_violations(); }
+long long agb_debug_event(int which) { return (long long)agb::debug_event(which); }
 
 }  /* extern "C" */

@@ -81,6 +81,8 @@ int jump_steps();
 void build_jump(const RngParams& prm, int steps, JumpTable* out);
 // bounds violations counted by the AGB_CHECK_BOUNDS build of the warp kernel (0 in release)
 unsigned long long debug_violations();
+// coverage counters of the same build (see playout_warp.cu); 0 in release
+unsigned long long debug_event(int which);
 
 // thread-per-playout kernel (playout_thread.cu)
 cudaError_t launch_playout_thread(int n, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info);

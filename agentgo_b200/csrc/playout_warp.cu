@@ -55,6 +55,14 @@ constexpr int kAmafRange = 40;      // AMAF_RANGE, GoContest/AgentGo.h:16
 // g_bounds_violations, which agb_debug_violations() returns; release builds index directly.
 #ifdef AGB_CHECK_BOUNDS
 __device__ unsigned long long g_bounds_violations;
+// coverage counters of the checked build (agb_debug_event): 0 = elist compactions forced by a full
+// array, 1 = compactions on entering / during complex mode, 2 = puts through the slow path
+__device__ unsigned long long g_debug_events[4];
+#define AGB_DEBUG_EVENT(k) do { if (lane == 0) atomicAdd(&g_debug_events[k], 1ull); } while (0)
+#else
+#define AGB_DEBUG_EVENT(k) do { } while (0)
+#endif
+#ifdef AGB_CHECK_BOUNDS
 template <typename T>
 struct SmemArr {
     T* p;
@@ -337,7 +345,7 @@ struct WarpBoard {
         if (spaces == 0) return -1;
         // Complex mode is sticky (game_ending, :348-351): the array is made dense once and then
         // kept current by put (zeroes the entry) and kill_string (appends).
-        if (n_dead < 0 || n_dead >= 8) { n_dead = 0; compact(); }      // 8 dead entries = one wasted round below
+        if (n_dead < 0 || n_dead >= 8) { AGB_DEBUG_EVENT(1); n_dead = 0; compact(); }      // 8 dead entries = one wasted round below
         int reserved_total = 0;
 #pragma unroll 1
         for (int base = 0; base < n_el; base += 8) {
@@ -459,7 +467,7 @@ struct WarpBoard {
         for (int k = root; k != kNilP;) {
             const int nx = fBh(h0[2 * k + 1]);
             stones--;
-            if (n_el == kElistCap) compact();                       // stale entries are dropped (never in complex mode)
+            if (n_el == kElistCap) { AGB_DEBUG_EVENT(0); compact(); }   // stale entries are dropped
             elist[n_el] = (uint16_t)k;                              // push at the list head, :311-321
             w0[k] = (uint32_t)n_el;                                 // empty, A = slot
             n_el++;
@@ -504,6 +512,15 @@ struct WarpBoard {
         // own and no own string with a liberty to spare, is filtered by both sampling phases and by
         // complex mode), so "no capture" alone selects the fast path; the slow path below would
         // also handle a self-capture, like the reference does.
+#ifdef AGB_CHECK_BOUNDS
+        {   // the invariant relied on above, checked: no capture => the new string has a liberty
+            int t = (frnd_l && first) ? left_l : 0;
+            t += __shfl_xor_sync(kFull, t, 1);
+            t += __shfl_xor_sync(kFull, t, 2);
+            if (captures == 0 && t + hp_self == 0 && lane == 0) atomicAdd(&g_bounds_violations, 1ull);
+            if (captures != 0) AGB_DEBUG_EVENT(2);
+        }
+#endif
         if (captures == 0) {
             // FAST PATH (no capture, ~88 % of the moves): everything the four sequential neighbour
             // steps of :129-167 do commutes except the unions, whose net effect is known in closed
@@ -830,6 +847,17 @@ cudaError_t launch_w(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchIn
 }
 
 }  // namespace
+
+unsigned long long debug_event(int which) {
+#ifdef AGB_CHECK_BOUNDS
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (which < 0 || which >= 4 || cudaMemcpyFromSymbol(v, g_debug_events, sizeof(v)) != cudaSuccess) return ~0ull;
+    return v[which];
+#else
+    (void)which;
+    return 0;
+#endif
+}
 
 unsigned long long debug_violations() {
 #ifdef AGB_CHECK_BOUNDS

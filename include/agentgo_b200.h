@@ -292,6 +292,11 @@ int agb_measure_peaks(int device, double* int_ops_per_s, double* int_ops_per_s_a
 /* Shared-memory bounds violations counted since load by the AGB_CHECK_BOUNDS build of the
  * kernels (`python -m agentgo_b200.build --debug`); always 0 in the release build.          */
 long long agb_debug_violations(void);
+/* Coverage counters of the same build: 0 = compactions of the empty-list array forced by a full
+ * array, 1 = compactions on entering / during complex mode, 2 = stones placed through the capture
+ * path of put.  The checked build also counts, as a violation, any move that breaks the invariant
+ * the release kernel relies on (a move of the policy is never a suicide).  0 in the release build. */
+long long agb_debug_event(int which);
 
 /* ---- the seed contract (shared verbatim by oracle and kernels) --------- */
 static inline uint32_t agb_playout_seed(uint64_t seed_base, uint32_t position_id,

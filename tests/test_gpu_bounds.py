@@ -14,6 +14,7 @@ pytestmark = pytest.mark.gpu
 SCRIPT = r"""
 import sys
 sys.path.insert(0, %r)
+sys.path.insert(1, sys.path[0] + '/tests')
 import numpy as np
 import agentgo_b200 as ag
 from oracle import pyoracle as po
@@ -26,6 +27,17 @@ for n, P in ((9, 600), (13, 300), (19, 300)):
     mv = po.OracleBoard(n, 'best').random_game(1, 2 * n * n, 99)
     e.replay(mv)
     e.playouts(2, None, P)
+# mid-game positions with many captures ahead: the empty-list array must fill up and be compacted
+from util import golden, split_moves
+pos = [(mv, 1 + len(mv) %% 2) for mv in split_moves(golden('midgame_19.npz'))]
+e = ag.Engine(19, kernel=ag.KERNEL_WARP)
+w, sp, sn, d, st = e.playouts_batch(pos, 400, want_diffs=True)
+for k in (0, 7, 15):
+    od = po.OracleBoard(19, 'best').replay(pos[k][0]).playouts(pos[k][1], None, 400, position_id=k, threads=0)[3]
+    assert (d[k] == od[0]).all()
+print('events', [ag.debug_event(k) for k in range(3)])
+assert ag.debug_event(1) > 0 and ag.debug_event(2) > 0
+assert ag.debug_event(0) > 0, 'the full-array compaction was never exercised'
 print('violations', ag.debug_violations())
 assert ag.debug_violations() == 0
 """
