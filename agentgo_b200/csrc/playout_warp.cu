@@ -213,16 +213,16 @@ struct WarpBoard {
     // checkSuicide/Kill/Survive/Dying/Chase/TrueEye/Compete (Board.cpp:480-755).
     //   bad     = dying | true eye | suicide | ko   (the filter of both sampling phases)
     //   reserve = true eye | suicide | ko           (complex mode: no checkDying, :425-427)
-    // Force-inlined at three call sites.  MODE selects what is computed, because the warp-sync
+    // Force-inlined at two call sites.  MODE selects what is computed, because the warp-sync
     // shuffles and ballots have side effects the compiler will not remove on its own:
     //   kEvalAll     neighbourhood phase: everything
     //   kEvalBad     rejection phase: `bad` only (no survive / chase: no fmin, fcap, eatari)
-    //   kEvalReserve complex mode: `reserve` only (additionally no friend sum)
+    // (Complex mode has many points to look at and uses one lane per point: reserved_point.)
     struct Eval {
         bool empty, kill, survive, chase, bad, reserve;
         bool live;      // kEvalAll only, warp-uniform: false = the early exit was taken, all masks are empty
     };
-    enum { kEvalAll = 0, kEvalBad = 1, kEvalReserve = 2 };
+    enum { kEvalAll = 0, kEvalBad = 1 };
     template <int MODE>
     __device__ __forceinline__ Eval eval_cells(int agent, int cidx) const {
         const unsigned nib = 15u << (lane & ~3);                    // this cell's four lanes
@@ -274,7 +274,7 @@ struct WarpBoard {
         const bool fsafe = (__ballot_sync(kFull, frnd && left > 0) & nib) != 0;
         const bool suicide = n_empty == 0 && !ecap && !fsafe;       // Board.cpp:480-524
         bool dying = false, survive = false, chase = false;
-        if (MODE != kEvalReserve) {
+        {
             int fsum = (frnd && first) ? left : 0;
             fsum += __shfl_xor_sync(kFull, fsum, 1);
             fsum += __shfl_xor_sync(kFull, fsum, 2);
@@ -336,8 +336,47 @@ struct WarpBoard {
         __syncwarp();
     }
 
+    // true eye | suicide | ko of the empty point idx for `agent` (checkTrueEye :735-751,
+    // checkSuicide :480-524, checkCompete :753-755; the reserve test of complex mode, :425-427),
+    // computed by ONE lane.  Complex mode looks at every empty point (50 on average), so a lane
+    // per point keeps all 32 lanes busy where eval_cells' four lanes per point would take four
+    // times as many rounds; nothing here is a warp collective.
+    __device__ __forceinline__ bool reserved_point(int agent, int idx) const {
+        const int offs[4] = {-W, -1, W, 1};
+        int root[4], hp[4], col[4];
+        int n_empty = 0;
+        bool edge = false, own4 = true;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            const uint32_t w = w0[idx + offs[d]];
+            col[d] = fCol(w);
+            n_empty += col[d] == 0;
+            edge |= col[d] == kBorder;
+            own4 &= col[d] == kBorder || col[d] == agent;
+            const bool stone = isStone(w);
+            root[d] = stone ? fA(w) : -1 - d;                       // distinct negatives per direction
+            hp[d] = (int)(w1[stone ? root[d] : 0] & 0xffffu);
+        }
+        // a string seen from several directions counts once, less its multiplicity (:506-515)
+        bool ecap = false, fsafe = false;
+#pragma unroll
+        for (int d = 0; d < 4; d++) {
+            int m = 0;
+#pragma unroll
+            for (int e = 0; e < 4; e++) m += root[e] == root[d];
+            ecap |= col[d] == 3 - agent && hp[d] == m;
+            fsafe |= col[d] == agent && hp[d] > m;
+        }
+        const bool suicide = n_empty == 0 && !ecap && !fsafe;
+        const int enemy = 3 - agent;
+        const int cnt = (fCol(w0[idx - W - 1]) == enemy) + (fCol(w0[idx - W + 1]) == enemy) +
+                        (fCol(w0[idx + W - 1]) == enemy) + (fCol(w0[idx + W + 1]) == enemy);
+        const bool eye = own4 && cnt < (edge ? 1 : 2);
+        return eye || suicide || ko_key == ((agent << 16) | idx);
+    }
+
     // Board::getRandomPieceComplex, Board.cpp:413-478.  Pass 1 (reserve flags, :419-433): the
-    // entries of elist are evaluated 8 per round with eval_cells and flagged in place.  Pass 2
+    // entries of elist are evaluated 32 per round, one lane each, and flagged in place.  Pass 2
     // (:445-470, the rnd-th unreserved point in list order) counts 32 entries per round from the
     // end of the array.
     __device__ __forceinline__ int random_piece_complex(int agent) {
@@ -345,16 +384,16 @@ struct WarpBoard {
         if (spaces == 0) return -1;
         // Complex mode is sticky (game_ending, :348-351): the array is made dense once and then
         // kept current by put (zeroes the entry) and kill_string (appends).
-        if (n_dead < 0 || n_dead >= 8) { AGB_DEBUG_EVENT(1); n_dead = 0; compact(); }      // 8 dead entries = one wasted round below
+        if (n_dead < 0 || n_dead >= 8) { AGB_DEBUG_EVENT(1); n_dead = 0; compact(); }
         int reserved_total = 0;
 #pragma unroll 1
-        for (int base = 0; base < n_el; base += 8) {
-            const int k = base + (lane >> 2);
-            const int idx = k < n_el ? (int)((uint32_t)elist[k] & 0x7fffu) : 0;     // 0 is a border cell
-            const Eval f = eval_cells<kEvalReserve>(agent, idx);
-            const bool res = f.empty && f.reserve;
-            if (f.empty && (lane & 3) == 0) elist[k] = (uint16_t)((uint32_t)idx | (res ? kResFlag : 0u));   // addReserve, :757-761
-            reserved_total += __popc(__ballot_sync(kFull, res) & 0x11111111u);
+        for (int base = 0; base < n_el; base += 32) {
+            const int k = base + lane;
+            const int ent = k < n_el ? (int)((uint32_t)elist[k] & 0x7fffu) : 0;    // 0: a dead entry
+            // dead entries look at some point of the board; their result is dropped
+            const bool res = reserved_point(agent, ent ? ent : W + 1) && ent != 0;
+            if (ent) elist[k] = (uint16_t)((uint32_t)ent | (res ? kResFlag : 0u));  // addReserve, :757-761
+            reserved_total += __popc(__ballot_sync(kFull, res));
         }
         __syncwarp();
         const int range = spaces - reserved_total;
