@@ -725,9 +725,10 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
 #endif
     bd.init_lane(lane);
 
-    unsigned long long moves = 0, draws = 0;
-    unsigned int faults = 0, played = 0;
-
+    // Nothing but the board state stays in registers across a playout: the statistics go out
+    // with one RED each per playout and the start descriptor is read again at the end (64
+    // registers per thread is what 32 resident warps leave; every register held here makes the
+    // compiler recompute lane constants inside the move loop instead).
 #pragma unroll 1
     for (;;) {
         unsigned long long l = 0;
@@ -738,7 +739,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         const int s = (int)(g / a.P);
         const int64_t p = g - (int64_t)s * a.P;
         const PaddedPosition& pos = a.pstarts[s];
-        const StartDesc d = a.descs[s];
+        const int first = a.descs[s].first;
 
         __syncwarp();
 #pragma unroll 1
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         bd.n_el = pos.n_el;
         bd.stones = pos.stones;
         bd.ko_key = pos.ko_key_col > 0 ? ((pos.ko_key_col << 16) | pos.ko_idx) : -1;
-        bd.prev = pos.last[2 - d.first];                            // last_move[enemy of the first mover]
+        bd.prev = pos.last[2 - first];                              // last_move[enemy of the first mover]
         bd.ending = pos.ending;
         if (lane < 8) bd.cbuf[lane] = (uint16_t)(WB::W + 1);        // any point of the board (see eval_cells)
         bd.pos = 0;
@@ -763,7 +764,8 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         __syncwarp();
         {
             // tinymt32_init (RFC 8682)
-            uint32_t st[4] = {playout_seed(a.seed_base, d.position_id, d.cand_idx, (uint64_t)p),
+            const StartDesc d0 = a.descs[s];
+            uint32_t st[4] = {playout_seed(a.seed_base, d0.position_id, d0.cand_idx, (uint64_t)p),
                               a.rng.mat1, a.rng.mat2, a.rng.tmat};
 #pragma unroll
             for (int i = 1; i < 8; i++)
@@ -780,7 +782,8 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
 
         // pair loop of MyWorker::work (AgentGo.cpp:295-325) / testAvrgWin (:422-443), one move
         // per iteration: the loop ends after a pair in which neither side moved.
-        int colour = d.first;
+        int colour = first;
+        const int amaf_agent = AMAF ? (int)a.descs[s].agent : 0;
         bool second = false;            // this move closes its pair
         bool first_moved = true, fault = false;
         uint32_t mv = 0;
@@ -796,7 +799,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
                     // mark[r] / mark2[r] = cstep of the FIRST play of that side at r (:304,:319);
                     // only cstep <= AMAF_RANGE is ever used
                     if (cstep <= kAmafRange) {
-                        const uint32_t key = (uint32_t)r | (colour == d.agent ? 512u : 0u);
+                        const uint32_t key = (uint32_t)r | (colour == amaf_agent ? 512u : 0u);
                         bool dup = false;
                         for (int b0 = 0; b0 < n_log; b0 += 32) {
                             const uint32_t e = b0 + lane < n_log ? amaf_log[b0 + lane] : 0xffffu;
@@ -820,11 +823,14 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             colour = 3 - colour;
         }
         __syncwarp();
+        const StartDesc d = a.descs[s];
         const int diff = fault ? -32768 : bd.score_diff(d.agent);
-        moves += mv;
-        draws += bd.pos;
-        played++;
-        if (fault) faults++;
+        if (lane == 0) {
+            atomicAdd(&a.stats[kStatMoves], (unsigned long long)mv);
+            atomicAdd(&a.stats[kStatDraws], (unsigned long long)bd.pos);
+            atomicAdd(&a.stats[kStatPlayouts], 1ull);
+            if (fault) atomicAdd(&a.stats[kStatFaults], 1ull);
+        }
         if (AMAF && !fault) {
             // :329-338 — point q counts for the agent table when the agent's first play there has
             // cstep <= 40, else for the enemy table when the enemy's has (the `else if`)
@@ -862,12 +868,6 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
                 }
             }
         }
-    }
-    if (lane == 0) {
-        atomicAdd(&a.stats[kStatMoves], moves);
-        atomicAdd(&a.stats[kStatDraws], draws);
-        if (faults) atomicAdd(&a.stats[kStatFaults], (unsigned long long)faults);
-        atomicAdd(&a.stats[kStatPlayouts], (unsigned long long)played);
     }
 }
 
