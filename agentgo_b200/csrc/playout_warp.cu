@@ -152,6 +152,12 @@ struct WarpBoard {
         const int cell = l >> 2;
         const int cc = cell + (cell >= 4);                          // skip the centre of the 3x3 block
         off_cell = (cc / 3 - 1) * W + (cc % 3 - 1);
+        // Opaque moves: without them the compiler recomputes these lane constants (two divisions
+        // by three for off_cell) at every use inside the move loop rather than hold a register.
+        asm volatile("mov.s32 %0, %0;" : "+r"(off_cell));
+        asm volatile("mov.s32 %0, %0;" : "+r"(off_nb));
+        asm volatile("mov.s32 %0, %0;" : "+r"(off_dg));
+        asm volatile("mov.s32 %0, %0;" : "+r"(lane));
     }
 
     // rand() number pos + i (i < kLookahead), without consuming it
