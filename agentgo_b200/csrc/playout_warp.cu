@@ -790,8 +790,9 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         // per iteration: the loop ends after a pair in which neither side moved.
         int colour = first;
         const int amaf_agent = AMAF ? (int)a.descs[s].agent : 0;
-        bool second = false;            // this move closes its pair
-        bool first_moved = true, fault = false;
+        int second = 0;                 // 1: this move closes its pair   (ints: the compiler packs bools
+        int first_moved = 1;            //                                 into bytes of one register)
+        bool fault = false;
         uint32_t mv = 0;
         int n_log = 0, cstep = 2;       // cstep is 2 in the first pair (:293,:297)
 #pragma unroll 1
@@ -819,13 +820,13 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             }
             bd.prev = r;                                            // Board.cpp:171 / :202
             if (second) {
-                if (!first_moved && r < 0) break;
+                if ((first_moved | (r >= 0)) == 0) break;
                 if ((int)mv > a.max_moves) { fault = true; break; } // fault detector, once per pair
                 if (AMAF) cstep++;
             } else {
                 first_moved = r >= 0;
             }
-            second = !second;
+            second ^= 1;
             colour = 3 - colour;
         }
         __syncwarp();
