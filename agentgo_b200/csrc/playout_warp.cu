@@ -178,7 +178,8 @@ struct WarpBoard {
     __device__ __forceinline__ void refill(const RngParams& prm, const JumpTable* __restrict__ jt) {
         const bool lo16 = lane < 16, lo8 = (lane & 8) == 0;
         const uint32_t sh = (lane & 7) * 4;
-        const uint4* __restrict__ row = &jt->e[lane * 16];
+        const uint4* __restrict__ tab = jt->e;
+        const uint32_t row = (uint32_t)lane * 16u;                  // 32-bit index: one IMAD.WIDE per lookup
         // The half of the ring about to be written is free (at most kLookahead draws are pending
         // and they sit in the other half), so the segment-start states are parked there: state l
         // in the first 16 bytes of lane l's own 32-byte segment, which that lane reads back before
@@ -189,7 +190,7 @@ struct WarpBoard {
         for (int l = 0; l < 32; l++) {
             park[2 * l] = make_uint4(g0, g1, g2, g3);
             const uint32_t word = lo16 ? (lo8 ? g0 : g1) : (lo8 ? g2 : g3);
-            const uint4 t = __ldg(&row[(word >> sh) & 15u]);
+            const uint4 t = __ldg(tab + (row | ((word >> sh) & 15u)));
             g0 = __reduce_xor_sync(kFull, t.x);
             g1 = __reduce_xor_sync(kFull, t.y);
             g2 = __reduce_xor_sync(kFull, t.z);
