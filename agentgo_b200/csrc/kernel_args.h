@@ -14,8 +14,9 @@ namespace agb {
 // in the state (links, roots, tails, last moves, ko point) is a padded index
 // p = (row+1)*(N+2) + (col+1).
 //
-//   w0 = A | B<<16 | colour<<30       (A and B are the two 16-bit halves of the word, so links and
-//                                      labels are rewritten with 16-bit stores, no read-modify-write)
+//   w0 = A | 4B<<16 | colour<<30      (A and 4B are the two 16-bit halves of the word, so links and
+//                                      labels are rewritten with 16-bit stores, no read-modify-write;
+//                                      B is kept times four = the byte offset of that stone's word)
 //        stone:  A = root index of its string,  B = next stone in the string (kNilP = end)
 //        empty:  A = slot of the point in `elist`, B = 0
 //   w1 = hp | tail<<16                at root stones

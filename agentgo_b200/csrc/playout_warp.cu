@@ -71,10 +71,10 @@ struct SmemArr {
         if ((unsigned)i >= (unsigned)n) { atomicAdd(&g_bounds_violations, 1ull); i = 0; }
         return p[i];
     }
-    // pointer to elements i, i+1 (both checked)
-    __device__ __forceinline__ T* pair(int i) const {
-        if ((unsigned)i + 1u >= (unsigned)n) { atomicAdd(&g_bounds_violations, 1ull); i = 0; }
-        return p + i;
+    // pointer to the two elements at byte offset `off` (both checked)
+    __device__ __forceinline__ T* pair_at(uint32_t off) const {
+        if (off / sizeof(T) + 1u >= (unsigned)n) { atomicAdd(&g_bounds_violations, 1ull); off = 0; }
+        return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + off);
     }
 };
 #else
@@ -82,26 +82,29 @@ template <typename T>
 struct SmemArr {
     T* p;
     __device__ __forceinline__ T& operator[](int i) const { return p[i]; }
-    __device__ __forceinline__ T* pair(int i) const { return p + i; }
+    __device__ __forceinline__ T* pair_at(uint32_t off) const { return reinterpret_cast<T*>(reinterpret_cast<char*>(p) + off); }
 };
 #endif
 
-// device word layout (kernel_args.h): A | B<<16 | colour<<30.  A and B are the 16-bit halves of the
+// device word layout (kernel_args.h): A | 4B<<16 | colour<<30.  A and B are the 16-bit halves of the
 // word, so labels and links are rewritten with 16-bit stores; the colour sits in the top two bits so
 // that it is one shift away and `empty` / `border` are plain compares on the word.
 __device__ __forceinline__ int fA(uint32_t w) { return (int)(w & 0xffffu); }
-__device__ __forceinline__ int fB(uint32_t w) { return (int)((w >> 16) & 511u); }
-__device__ __forceinline__ int fBh(uint32_t hi) { return (int)(hi & 511u); }          // from the high half
+// B is stored times four (the byte offset of the next stone's word), so a walk along a string
+// turns the loaded half word into the next address with one AND
+__device__ __forceinline__ int fBh(uint32_t hi) { return (int)((hi >> 2) & 511u); }   // from the high half
+__device__ __forceinline__ uint32_t offB(uint32_t hi) { return hi & 0x7fcu; }         // byte offset of B's word
+constexpr uint32_t kNilOff = 4u * kNilP;
 __device__ __forceinline__ int fCol(uint32_t w) { return (int)(w >> 30); }
 __device__ __forceinline__ bool isEmpty(uint32_t w) { return w < 0x40000000u; }
 __device__ __forceinline__ bool isBorder(uint32_t w) { return w >= 0xc0000000u; }
 // colour 1 or 2: adding a quarter turn moves exactly those two into the upper half of the range
 __device__ __forceinline__ bool isStone(uint32_t w) { return (int32_t)(w + 0x40000000u) < 0; }
 __device__ __forceinline__ uint32_t pack0(int a, int b, int col) {
-    return (uint32_t)a | ((uint32_t)b << 16) | ((uint32_t)col << 30);
+    return (uint32_t)a | ((uint32_t)b << 18) | ((uint32_t)col << 30);
 }
 // high half of a stone's word: colour and next-in-string link
-__device__ __forceinline__ uint16_t packHi(int b, int col) { return (uint16_t)((uint32_t)b | ((uint32_t)col << 14)); }
+__device__ __forceinline__ uint16_t packHi(int b, int col) { return (uint16_t)(((uint32_t)b << 2) | ((uint32_t)col << 14)); }
 constexpr uint32_t kResFlag = 0x8000u;     // elist entry: point is reserved in the current complex-mode call
 
 template <int N>
@@ -607,24 +610,25 @@ struct WarpBoard {
                 if (!(others & (others - 1u))) {
                     // the usual case of a merge: one string, walked warp-uniformly
                     const int d1 = __ffs(others) - 1;
-                    const int t1 = (int)(__shfl_sync(kFull, h_l, d1) >> 16);
+                    const uint32_t t1 = 4u * (__shfl_sync(kFull, h_l, d1) >> 16);
 #pragma unroll 1
-                    for (int sidx = __shfl_sync(kFull, root_l, d1);;) {
-                        uint16_t* c = h0.pair(2 * sidx);            // one address for both halves
+                    for (uint32_t off = 4u * (uint32_t)__shfl_sync(kFull, root_l, d1);;) {
+                        uint16_t* c = h0.pair_at(off);              // both halves of the stone's word
                         c[0] = (uint16_t)fk;
-                        if (sidx == t1) break;
-                        sidx = fBh(c[1]);
+                        if (off == t1) break;
+                        off = offB(c[1]);
                     }
                 } else {
                     // two or three strings: each is walked by its own lane
                     bool walk = own_l && root_l != fk;
-                    int sidx = root_l;
+                    uint32_t off = walk ? 4u * (uint32_t)root_l : 0u;
 #pragma unroll 1
                     while (__ballot_sync(kFull, walk)) {
                         if (walk) {
-                            h0[2 * sidx] = (uint16_t)fk;
-                            walk = sidx != tail_l;
-                            sidx = fBh(h0[2 * sidx + 1]);
+                            uint16_t* c = h0.pair_at(off);
+                            c[0] = (uint16_t)fk;
+                            walk = off != 4u * (uint32_t)tail_l;
+                            off = offB(c[1]);
                         }
                     }
                 }
@@ -659,10 +663,10 @@ struct WarpBoard {
                         w1[sn] = ((h + h2) & 0xffffu) | (h2 & 0xffff0000u);
                         h0[2 * t1 + 1] = packHi(s2, agent);
 #pragma unroll 1
-                        for (int k = s2; k != kNilP;) {
-                            uint16_t* c = h0.pair(2 * k);
+                        for (uint32_t off = 4u * (uint32_t)s2; off != kNilOff;) {
+                            uint16_t* c = h0.pair_at(off);
                             c[0] = (uint16_t)sn;
-                            k = fBh(c[1]);
+                            off = offB(c[1]);
                         }
                     }
                 }
@@ -926,7 +930,7 @@ void to_padded(const Position& p, PaddedPosition* out) {
         const int col = (int)((v0 >> 20) & 3u);
         const int a = (int)(v0 & 1023u), b = (int)((v0 >> 10) & 1023u);
         if (col == 0) { out->w0[pad(idx)] = 0; continue; }         // the slot is filled in below
-        out->w0[pad(idx)] = (uint32_t)pad(a) | ((uint32_t)(b == kNil ? kNilP : pad(b)) << 16) | ((uint32_t)col << 30);
+        out->w0[pad(idx)] = (uint32_t)pad(a) | ((uint32_t)(b == kNil ? kNilP : pad(b)) << 18) | ((uint32_t)col << 30);
         const bool is_root = a == idx;                              // hp/tail are meaningful at roots only
         out->w1[pad(idx)] = is_root ? ((v1 & 0xffffu) | ((uint32_t)pad((int)(v1 >> 16)) << 16)) : 0u;
     }
