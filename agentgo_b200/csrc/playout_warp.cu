@@ -135,7 +135,8 @@ struct WarpBoard {
     SmemArr<uint16_t> ring;      // kRing entries, entry (p & (kRing-1)) holds draw number p of this playout;
                                  // then kMirror more that repeat the first kMirror, so that a read of
                                  // up to kMirror draws ahead of pos needs no wrap-around per lane
-    uint32_t g0, g1, g2, g3;     // generator state at draw number gen_end (warp-uniform)
+    uint4* gstate;               // generator state at draw number gen_end: only a refill needs it, so it
+                                 // lives in shared memory, not in four registers of the move loop
     uint32_t pos;                // next draw to be consumed = rand() calls made so far
     uint32_t gen_end;            // draws [pos, gen_end) are in the ring
 
@@ -189,6 +190,11 @@ struct WarpBoard {
         // it writes its draws over it.  (A register capture costs a compare and four selects per
         // step in all lanes; this is one store.)
         uint4* park = reinterpret_cast<uint4*>(ring.p + (gen_end & (kRing - 1)));
+        uint32_t g0, g1, g2, g3;
+        {
+            const uint4 g = *gstate;
+            g0 = g.x; g1 = g.y; g2 = g.z; g3 = g.w;
+        }
 #pragma unroll 4
         for (int l = 0; l < 32; l++) {
             park[2 * l] = make_uint4(g0, g1, g2, g3);
@@ -213,6 +219,7 @@ struct WarpBoard {
             ring[base + j] = v;
             if (mirrored) ring[kRing + base + j] = v;
         }
+        *gstate = make_uint4(g0, g1, g2, g3);
         gen_end += kRefill;
         __syncwarp();
     }
@@ -702,12 +709,13 @@ struct WarpBoard {
     }
 };
 
-// per-warp shared memory in words: w0[NP], w1[NP], elist[kElistCap] and cand[8] (16 bit), rounded
-// to 32 words, then the ring of kRing 16-bit draws
+// per-warp shared memory in words: w0[NP], w1[NP], elist[kElistCap] and cand[8] (16 bit), the
+// generator state (4 words), rounded to 32 words, then the ring of kRing 16-bit draws
 template <int N>
 struct BoardWords {
     static constexpr int NP = (N + 2) * (N + 2);
-    static constexpr int board = ((2 * NP + kElistCap / 2 + 4 + 31) / 32) * 32;
+    static constexpr int gstate = ((2 * NP + kElistCap / 2 + 4 + 3) / 4) * 4;     // 4 words, 16-byte aligned
+    static constexpr int board = ((gstate + 4 + 31) / 32) * 32;
     static constexpr int value = board + (WarpBoard<N>::kRing + WarpBoard<N>::kMirror) / 2;
     static constexpr int kAmafLog = 80;                     // first plays with cstep <= 40: at most 78
     static constexpr int value_amaf = value + kAmafLog / 2;
@@ -730,6 +738,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
     bd.h0.p = reinterpret_cast<uint16_t*>(base);
     bd.elist.p = reinterpret_cast<uint16_t*>(base + 2 * WB::NP);
     bd.cbuf.p = bd.elist.p + kElistCap;
+    bd.gstate = reinterpret_cast<uint4*>(base + BoardWords<N>::gstate);
     bd.ring.p = reinterpret_cast<uint16_t*>(base + BoardWords<N>::board);
 #ifdef AGB_CHECK_BOUNDS
     bd.w0.n = WB::NP; bd.w1.n = WB::NP; bd.h0.n = 2 * WB::NP; bd.elist.n = kElistCap; bd.cbuf.n = 8; bd.ring.n = WB::kRing + WB::kMirror;
@@ -788,7 +797,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             t.s0 = st[0]; t.s1 = st[1]; t.s2 = st[2]; t.s3 = st[3];
 #pragma unroll 1
             for (int i = 0; i < 8; i++) t.next_state(a.rng.mat1, a.rng.mat2);
-            bd.g0 = t.s0; bd.g1 = t.s1; bd.g2 = t.s2; bd.g3 = t.s3;
+            *bd.gstate = make_uint4(t.s0, t.s1, t.s2, t.s3);
         }
 
         // pair loop of MyWorker::work (AgentGo.cpp:295-325) / testAvrgWin (:422-443), one move
