@@ -164,20 +164,22 @@ class OracleBoard:
                                  out.ctypes.data_as(C.POINTER(C.c_uint32)))
         return out
 
-    def playouts_amaf(self, colour, cands, P, avrg_win=0, seed_base=20151001, position_id=0):
+    def playouts_amaf(self, colour, cands, P, avrg_win=0, seed_base=20151001, position_id=0, per_candidate=False):
         """Candidate-mode playouts with AMAF first-play marks (AgentGo.cpp:286-338).
         returns (wins, sum_pos, sum_neg, amaf) with amaf int64 [2 which][2 sign][41 step][NN],
-        accumulated over all candidates like the reference's global amaf1/amaf2."""
+        accumulated over all candidates like the reference's global amaf1/amaf2, or one such table
+        per candidate ([C, 2, 2, 41, NN]) when per_candidate is set."""
         nn = self.n * self.n
         out3 = np.zeros((len(cands), 3), dtype=np.int64)
-        amaf = np.zeros((2, 2, AMAF_RANGE + 1, nn), dtype=np.int64)
+        amaf = np.zeros((len(cands) if per_candidate else 1, 2, 2, AMAF_RANGE + 1, nn), dtype=np.int64)
         for c, (row, col) in enumerate(cands):
+            tab = amaf[c if per_candidate else 0]
             r = self.lib.orc_playouts_amaf(self.h, colour, row, col, position_id, c, 0, P, 1, seed_base, avrg_win,
                                            out3[c].ctypes.data_as(C.POINTER(C.c_int64)),
-                                           amaf.ctypes.data_as(C.POINTER(C.c_int64)))
+                                           tab.ctypes.data_as(C.POINTER(C.c_int64)))
             if r:
                 raise RuntimeError("orc_playouts_amaf -> %d" % r)
-        return out3[:, 0].copy(), out3[:, 1].copy(), out3[:, 2].copy(), amaf
+        return out3[:, 0].copy(), out3[:, 1].copy(), out3[:, 2].copy(), (amaf if per_candidate else amaf[0])
 
     def playouts(self, colour, cands, P, avrg_win=0, seed_base=20151001, position_id=0,
                  want_diffs=True, threads=1, with_stats=False):

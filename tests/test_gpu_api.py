@@ -124,7 +124,7 @@ def test_edge_cases(built_lib):
     assert (e2.export_state() == ob.export_state()).all()
 
 
-def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base, use_amaf=False):
+def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base, use_amaf=False, moves=()):
     w, sp, sn, _ = ob.playouts(colour, None, P_root, seed_base=seed_base, want_diffs=False, threads=0)
     tot = int(sp[0] + sn[0])
     avrg = abs(tot) // P_root * (1 if tot >= 0 else -1)          # C truncation, AgentGo.cpp:447
@@ -141,16 +141,23 @@ def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base, use_amaf=False):
     if cands:
         cnsv = 2.0 ** (avrg * 0.01)
         if use_amaf:
-            w, sp, sn, A = ob.playouts_amaf(colour, cands, P_cand, avrg_win=avrg, seed_base=seed_base + 1)
-            num_piece = int(st[1] + st[2]) + 1
-            num_a = 1.0 / (40.0 - (39.0 / 180) * num_piece)
-            num_b = 0.3 - (0.3 / 180) * num_piece
-            for s in range(2, 41):
-                k = s - 1
-                base = num_a * k
-                v = 1 - (base ** num_b if base >= 0 else float("nan"))
-                v = 0.0 if not (v >= 0) else min(v, 1.0)
-                amaf12 += 100.0 * v * ((A[0, 0, s] + cnsv * A[0, 1, s]) - (A[1, 0, s] + cnsv * A[1, 1, s]))
+            w, sp, sn, Ac = ob.playouts_amaf(colour, cands, P_cand, avrg_win=avrg, seed_base=seed_base + 1,
+                                             per_candidate=True)
+            for (ci, cj), A in zip(cands, Ac):
+                # the decay table is recomputed per candidate from the stones AFTER it is played
+                # (AgentGo.cpp:84-94): a candidate that captures sees fewer
+                after = po.OracleBoard(n, "best").replay(moves)
+                after.put(colour, ci, cj)
+                sa = after.export_state()
+                num_piece = int(sa[1] + sa[2])
+                num_a = 1.0 / (40.0 - (39.0 / 180) * num_piece)
+                num_b = 0.3 - (0.3 / 180) * num_piece
+                for s in range(2, 41):
+                    k = s - 1
+                    base = num_a * k
+                    v = 1 - (base ** num_b if base >= 0 else float("nan"))
+                    v = 0.0 if not (v >= 0) else min(v, 1.0)
+                    amaf12 += 100.0 * v * ((A[0, 0, s] + cnsv * A[0, 1, s]) - (A[1, 0, s] + cnsv * A[1, 1, s]))
         else:
             w, sp, sn, _ = ob.playouts(colour, cands, P_cand, avrg_win=avrg, seed_base=seed_base + 1, want_diffs=False, threads=0)
         for c, a, b in zip(cands, sp, sn):
@@ -178,7 +185,7 @@ def test_genmove_matches_oracle_restatement(built_lib):
         # with the AMAF terms of AgentGo.cpp:329-338,654-655
         e2 = ag.Engine(n, genmove_amaf=1).replay(mv)
         got2, _ = e2.genmove(colour, 60, 200, seed_base=777)
-        assert got2 == _oracle_genmove(ob, n, colour, 60, 200, 777, use_amaf=True)
+        assert got2 == _oracle_genmove(ob, n, colour, 60, 200, 777, use_amaf=True, moves=mv)
 
 
 def test_full_size_config2_bit_exact(built_lib):
@@ -231,3 +238,36 @@ def test_move_cap_is_reported_as_fault(built_lib, kernel):
     # the engine stays usable afterwards
     e2 = ag.Engine(9, kernel=kernel)
     assert e2.playouts(ag.BLACK, None, 64)[4]["faults"] == 0
+
+
+def test_ragged_batch_and_wide_candidate_sets(built_lib):
+    """Ragged inputs and the widest candidate set: a batch mixing an empty move list, a list with
+    passes and long games; every empty point of a 19x19 position as a candidate with P = 1 and 2."""
+    n = 19
+    games = [np.zeros(0, dtype=np.uint32),
+             np.array([ag.move(1, 3, 3), ag.move_pass(2), ag.move(1, 15, 15), ag.move_pass(2), ag.move_pass(1)], dtype=np.uint32),
+             po.OracleBoard(n, "best").random_game(1, 1, 5),
+             po.OracleBoard(n, "best").random_game(2, 333, 6),
+             po.OracleBoard(n, "best").random_game(1, 700, 7)]
+    pos = [(mv, 1 + k % 2) for k, mv in enumerate(games)]
+    e = ag.Engine(n)
+    P = 200
+    w, sp, sn, d, st = e.playouts_batch(pos, P, seed_base=4242, first_position_id=10, want_diffs=True)
+    assert st["playouts"] == len(pos) * P and st["faults"] == 0
+    for k, (mv, colour) in enumerate(pos):
+        ob = po.OracleBoard(n, "best").replay(mv)
+        ow, osp, osn, od = ob.playouts(colour, None, P, seed_base=4242, position_id=10 + k, threads=0)
+        assert (d[k] == od[0]).all(), k
+        assert (w[k], sp[k], sn[k]) == (ow[0], osp[0], osn[0])
+    # every empty point of a mid-game position as a candidate (suicides included: the candidate
+    # stone is placed by the host's put, which handles self-capture like the reference)
+    mv = po.OracleBoard(n, "best").random_game(2, 150, 8)
+    ob = po.OracleBoard(n, "best").replay(mv)
+    st0 = ob.export_state()
+    cands = [(i // n, i % n) for i in range(n * n) if st0[16 + i] == 0]
+    assert len(cands) > 100
+    e = ag.Engine(n).replay(mv)
+    for P in (1, 2):
+        w, sp, sn, d, st = e.playouts(ag.WHITE, cands, P, avrg_win=-2, seed_base=9, want_diffs=True)
+        ow, osp, osn, od = ob.playouts(2, cands, P, avrg_win=-2, seed_base=9, threads=0)
+        assert (d == od).all() and (w == ow).all() and (sp == osp).all() and (sn == osn).all()
