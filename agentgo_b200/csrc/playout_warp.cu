@@ -6,10 +6,12 @@
 //
 //  * The board is padded to (N+2)x(N+2) with a border of colour 3 (PaddedPosition,
 //    kernel_args.h): neighbour and diagonal reads need no bounds checks, and every stored index
-//    (links, roots, tails, head, last moves, ko point) is a padded index.
-//  * State updates (put / capture / merge / pass) run WARP-UNIFORM: every lane executes the
-//    same scalar code on the same shared-memory words (same address, same value), so there is
-//    no divergence and no intra-warp communication.
+//    (links, roots, tails, last moves, ko point) is a padded index.  The reference's linked list
+//    of empty points is an append-only array here (kernel_args.h): placing a stone costs nothing.
+//  * State updates (put / capture / merge / pass): the 88 % of moves that capture nothing take a
+//    lane-parallel path (one lane per direction); a capture makes the reference's sequential
+//    order observable and runs WARP-UNIFORM — every lane executes the same scalar code on the
+//    same shared-memory words (same address, same value), no divergence, no communication.
 //  * The policy's predicates are evaluated LANE-PARALLEL: lane = (cell, direction) with
 //    8 cells x 4 directions = 32 lanes (eval_cells).
 //  * RANDOM NUMBERS ARE DECOUPLED FROM THEIR CONSUMPTION.  The reference consumes one serial
@@ -31,15 +33,20 @@
 //    moves) just advance the read position by 18.  Rejection phase: 32 (row, col) pairs per
 //    round, the empty ones are evaluated in draw order, 8 per eval_cells call; the 100th draw
 //    is never accepted (Board.cpp:402-405).
-//  * Clone, scoring and the complex-mode legality pass are strided over the lanes; complex mode
-//    first compacts the empty points with ballots.
+//  * Clone and scoring are strided over the lanes.  Complex mode (Board::getRandomPieceComplex)
+//    looks at every empty point, 50 on average: ONE LANE PER POINT (reserved_point, no
+//    collectives), and its ordered walk counts 32 entries of the empty-point array per ballot.
+//  * 64 registers per thread is what 32 resident warps leave.  Nothing but board state lives in
+//    registers across a playout, the generator state is parked in shared memory between refills,
+//    and the lane constants are pinned with opaque moves: the compiler otherwise recomputes them
+//    inside the move loop (profiles/README.md, v22/v23).
 //
 // The code is written for a SMALL INSTRUCTION FOOTPRINT: 32 warps per SM sit at 32 different
 // program counters, and the first version of this kernel (every helper force-inlined, both
 // movers unrolled: 6 150 SASS instructions, 98 KB) spent 70 % of its stall samples waiting for
 // instruction fetch (profiles/r01_warp_v1_*.txt).  Hence: one move loop for both colours, one
 // capture site, one complex-mode site, rolled loops.  Since then the kernel is bound by the
-// integer ALU pipe (profiles/r01_warp_v3_*.txt), so the remaining lever is instruction count.
+// integer ALU pipe and the issue slots (80 % busy), so the remaining lever is instruction count.
 #include "kernel_args.h"
 
 namespace agb {
