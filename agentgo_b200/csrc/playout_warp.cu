@@ -39,7 +39,7 @@
 //  * 64 registers per thread is what 32 resident warps leave.  Nothing but board state lives in
 //    registers across a playout, the generator state is parked in shared memory between refills,
 //    and the lane constants are pinned with opaque moves: the compiler otherwise recomputes them
-//    inside the move loop (profiles/README.md, v22/v23).
+//    inside the move loop.
 //
 // The code is written for a SMALL INSTRUCTION FOOTPRINT: 32 warps per SM sit at 32 different
 // program counters, and the first version of this kernel (every helper force-inlined, both
