@@ -245,6 +245,7 @@ struct WarpBoard {
     struct Eval {
         bool empty, kill, survive, chase, bad, reserve;
         bool live;      // kEvalAll only, warp-uniform: false = the early exit was taken, all masks are empty
+        bool easy0;     // kEvalBad only, warp-uniform: cell 0 was accepted by the early test
     };
     enum { kEvalAll = 0, kEvalBad = 1 };
     template <int MODE>
@@ -267,6 +268,7 @@ struct WarpBoard {
                 Eval z;
                 z.empty = true; z.kill = z.survive = z.chase = z.reserve = false;
                 z.bad = lane >= 4;
+                z.easy0 = true;
                 return z;
             }
         }
@@ -288,7 +290,7 @@ struct WarpBoard {
             // the neighbourhood phase are empty and nothing else matters (~70 % of the calls)
             if (__ballot_sync(kFull, isEmpty(wc) && nb_stone && left <= 1) == 0) {
                 Eval z;
-                z.empty = z.kill = z.survive = z.chase = z.bad = z.reserve = z.live = false;
+                z.empty = z.kill = z.survive = z.chase = z.bad = z.reserve = z.live = z.easy0 = false;
                 return z;
             }
         }
@@ -332,6 +334,7 @@ struct WarpBoard {
         e.reserve = eye || suicide || ko;
         e.bad = e.reserve || dying;
         e.live = true;
+        e.easy0 = false;
         return e;
     }
 
@@ -504,6 +507,11 @@ struct WarpBoard {
                     const int cell = lane >> 2;
                     const uint32_t entry = cbuf[cell];          // cells >= ncand: a stale or the initial point, unused
                     const Eval e = eval_cells<kEvalBad>(agent, (int)(entry & 511u));
+                    if (e.easy0) {                              // the first candidate in draw order, held by lane 0
+                        const uint32_t win = __shfl_sync(kFull, entry, 0);
+                        pos += 2 * ((win >> 9) + 1);
+                        return (int)(win & 511u);
+                    }
                     const unsigned good = __ballot_sync(kFull, cell < ncand && !e.bad);
                     if (good) {
                         const uint32_t win = __shfl_sync(kFull, entry, __ffs(good) - 1);
