@@ -71,6 +71,15 @@ def test_multi_gpu_selfplay_equals_single_gpu(built_lib):
         assert r.returncode == 0, r.stderr
         games.append([l for l in r.stderr.splitlines() if l[:3].strip().isdigit()])
     assert len(games[0]) == 60 and games[0] == games[1]
+    # the same with the reference's complete policy (book, static marks, AMAF tables split by the
+    # stones a candidate leaves) at the reference's board size
+    games = []
+    for gpus in ("1", "2"):
+        r = subprocess.run([GTP, "--boardsize", "13", "--selfplay", "--playouts", "30", "--root-playouts", "60",
+                            "--max-moves", "50", "--gpus", gpus, "--reference-policy"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr
+        games.append([l for l in r.stderr.splitlines() if l[:3].strip().isdigit()])
+    assert len(games[0]) == 50 and games[0] == games[1]
 
 
 @pytest.mark.gpu
