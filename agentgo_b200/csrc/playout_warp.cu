@@ -459,8 +459,11 @@ struct WarpBoard {
         }
         if (!complex_mode) {
             n_dead = -1;                                            // put stops maintaining elist
-            const int lm = prev;                                    // opponent's last move
-            if (lm >= 0 && fCol(w0[lm]) == 3 - agent) {             // :355-380
+            // opponent's last move.  The reference also requires the stone to be still there
+            // (:356); inside a playout it always is (it was placed one move ago), and for the first
+            // move of a playout the kernel settles that before the loop.
+            const int lm = prev;
+            if (lm >= 0) {                                          // :355-380
                 const Eval f = eval_cells<kEvalAll>(agent, lm + off_cell);
                 unsigned K = 0, S = 0, C = 0;
                 if (f.live) {
@@ -793,6 +796,9 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         bd.prev = pos.last[2 - first];                              // last_move[enemy of the first mover]
         bd.ending = pos.ending;
         if (lane < 8) bd.cbuf[lane] = (uint16_t)(WB::W + 1);        // any point of the board (see eval_cells)
+        __syncwarp();
+        // Board.cpp:356 for the first move: the opponent's last stone may have been captured since
+        if (bd.prev >= 0 && fCol(bd.w0[bd.prev]) != 3 - first) bd.prev = -1;
         bd.pos = 0;
         bd.gen_end = 0;
         bd.n_dead = -1;
