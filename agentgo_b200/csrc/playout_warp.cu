@@ -825,8 +825,6 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         // per iteration: the loop ends after a pair in which neither side moved.
         int colour = first;
         const int amaf_agent = AMAF ? (int)a.descs[s].agent : 0;
-        int second = 0;                 // 1: this move closes its pair   (ints: the compiler packs bools
-        int first_moved = 1;            //                                 into bytes of one register)
         bool fault = false;
         uint32_t mv = 0;
         int n_log = 0, cstep = 2;       // cstep is 2 in the first pair (:293,:297)
@@ -853,15 +851,15 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             } else {                                                // Board::pass, Board.cpp:200-203
                 bd.ko_key = -1;
             }
+            // the move that closes a pair (the second mover's) ends the playout when neither side
+            // moved: the first mover's move is what prev still holds, -1 for a pass
+            const int before = bd.prev;
             bd.prev = r;                                            // Board.cpp:171 / :202
-            if (second) {
-                if ((first_moved | (r >= 0)) == 0) break;
+            if (colour != first) {
+                if ((before & r) < 0) break;
                 if ((int)mv > a.max_moves) { fault = true; break; } // fault detector, once per pair
                 if (AMAF) cstep++;
-            } else {
-                first_moved = r >= 0;
             }
-            second ^= 1;
             colour = 3 - colour;
         }
         __syncwarp();
