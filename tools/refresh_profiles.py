@@ -22,7 +22,8 @@ fill = [v for k, v in per.items() if "FillFunctor" in k[1]]
 m = dict(l.strip().split(" = ") for l in open("profiles/r01_warp_%s_metrics.txt" % tag) if " = " in l)
 inst = [float(v) for k, v in m.items() if k.startswith("smsp__inst_executed.sum")][0]
 ipc = [float(v) for k, v in m.items() if k.startswith("sm__inst_executed.avg.per_cycle_elapsed")][0]
-traffic = statistics.mean(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in play)
+# median: a launch that follows the 256 MiB L2-flush fill sometimes absorbs the write-back of its dirty lines
+traffic = statistics.median(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in play)
 dur = statistics.mean(v["gpu__time_duration.sum"] for v in play) / 1e6
 fd = statistics.mean(v["gpu__time_duration.sum"] for v in fill) / 1e6
 json.dump({"kernel": "playout_warp_kernel<19,8,4,false>", "launches": len(play), "dram_bytes_per_launch": traffic,
