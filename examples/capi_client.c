@@ -59,6 +59,15 @@ int main(int argc, char** argv) {
     for (i = 0; i < C; i++)
         printf("cand %d %d wins=%lld sum_pos=%lld sum_neg=%lld\n", cand[2 * i], cand[2 * i + 1],
                (long long)wins[i], (long long)sum_pos[i], (long long)sum_neg[i]);
+    if (C > 0) {
+        /* static pattern marks of MyWorker::work for the first candidate (AgentGo.cpp:104-282) and the
+         * score of the position the way the reference's match harness counts it (GeneHatchery.cpp:393) */
+        int64_t ua = 0, ub = 0;
+        int dscore = 0;
+        if (agb_static_units(h, AGB_BLACK, cand[0], cand[1], &ua, &ub) != AGB_OK || agb_calc_result(h, &dscore) != AGB_OK)
+            return 1;
+        printf("static %d %d units_a=%lld units_b=%lld calc_result=%d\n", cand[0], cand[1], (long long)ua, (long long)ub, dscore);
+    }
     if (agb_genmove(h, AGB_BLACK, 150, 500, 20151001ull, &row, &col, &is_pass, NULL) != AGB_OK) return 1;
     printf("genmove row=%d col=%d pass=%d\n", row, col, is_pass);
     agb_destroy(h);

@@ -36,5 +36,7 @@ def test_c_client_matches_python_mirror(built_lib):
     w, sp, sn, _, _ = e.playouts(ag.BLACK, cands, 150, avrg_win=avrg, seed_base=20151002)
     for l, a, b, c in zip([l for l in lines if l.startswith("cand ")], w, sp, sn):
         assert l.endswith("wins=%d sum_pos=%d sum_neg=%d" % (a, b, c))
+    ua, ub = e.static_units(ag.BLACK, *cands[0])
+    assert lines[-2] == "static %d %d units_a=%d units_b=%d calc_result=%d" % (cands[0] + (ua, ub, e.calc_result()))
     mv, _ = e.genmove(ag.BLACK, 150, 500, seed_base=20151001)
     assert lines[-1] == "genmove row=%d col=%d pass=0" % mv
