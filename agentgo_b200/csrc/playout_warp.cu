@@ -489,15 +489,14 @@ struct WarpBoard {
                 }
                 pos += 18;      // nine iterations, two draws each, none accepted
             }
-            // rejection loop, :382-406: pairs count+1 .. count+B are examined in one round
+            // rejection loop, :382-406: up to 32 pairs are examined in one round.  lim = the pairs
+            // that may still be accepted: the 100th draw is consumed but never accepted (:402-405)
 #pragma unroll 1
-            for (int count = 0; count < kEndingThreshold;) {
-                const int B = min(32, kEndingThreshold - count);
-                const int A = min(32, kEndingThreshold - 1 - count);    // the 100th draw is never accepted (:402-405)
+            for (int lim = kEndingThreshold - 1; lim >= 0;) {
                 const uint32_t row = mod_small<N>(peek(2 * lane));
                 const uint32_t cl = mod_small<N>(peek(2 * lane + 1));
                 const int idx = (int)(row * W + cl + (W + 1));
-                const bool can = lane < A && isEmpty(w0[idx]);
+                const bool can = lane < lim && isEmpty(w0[idx]);
                 unsigned cand = __ballot_sync(kFull, can);
                 // evaluate the empty candidates in draw order, 8 per round
 #pragma unroll 1
@@ -524,8 +523,9 @@ struct WarpBoard {
                     cand &= ~__ballot_sync(kFull, mine);
                     __syncwarp();
                 }
+                const int B = min(32, lim + 1);                         // pairs consumed by this round
                 pos += 2 * B;
-                count += B;
+                lim -= B;
             }
             ending = 1;
         }
