@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AGB_LIB", os.path.join(HERE, "libagentgo_b200.so"))
 
 EMPTY, BLACK, WHITE = 0, 1, 2
-KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP = 0, 1, 2
+KERNEL_AUTO, KERNEL_THREAD, KERNEL_WARP, KERNEL_GROUP8, KERNEL_GROUP16, KERNEL_GROUP32 = 0, 1, 2, 3, 4, 5
 ROOT_CANDIDATE = 0xFFFFFFFF
 AMAF_RANGE = 40
 CHECKS = {"suicide": 0, "kill": 1, "survive": 2, "dying": 3, "chase": 4,

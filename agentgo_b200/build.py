@@ -11,7 +11,8 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(HERE, "..", "include")
 LIB = os.path.join(HERE, "libagentgo_b200.so")
 GTP = os.path.join(HERE, "agentgo_gtp")
-SOURCES = ["host_board.cpp", "engine.cu", "playout_thread.cu", "playout_warp.cu", "diag.cu", "capi.cpp", "nccl_group.cpp"]
+SOURCES = ["host_board.cpp", "host_layout.cpp", "engine.cu", "playout_thread.cu", "playout_warp.cu", "playout_group.cu",
+           "diag.cu", "capi.cpp", "nccl_group.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", CSRC, "-I", INCLUDE]

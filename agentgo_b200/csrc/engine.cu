@@ -123,12 +123,20 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     const bool thread_kernel = cfg.kernel == AGB_KERNEL_THREAD;
     if (want_amaf && thread_kernel)
         return fail(AGB_ERR_INVALID, "AMAF marks are implemented by the warp kernel only");
+    // lanes per playout of the group kernel, 0 = another kernel.  AMAF marks are recorded by the
+    // warp kernel.
+    int group_lanes = 0;
+    if (!want_amaf) {
+        if (cfg.kernel == AGB_KERNEL_GROUP8 || cfg.kernel == AGB_KERNEL_AUTO) group_lanes = 8;
+        else if (cfg.kernel == AGB_KERNEL_GROUP16) group_lanes = 16;
+        else if (cfg.kernel == AGB_KERNEL_GROUP32) group_lanes = 32;
+    }
     const size_t amaf_bytes = sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n()) * (size_t)amaf_classes();
     if (want_amaf) {
         if ((st = ensure(&d_amaf_, &cap_amaf_, amaf_bytes))) return st;
         AGB_CUDA(cudaMemsetAsync(d_amaf_, 0, amaf_bytes, stream_));
     }
-    const size_t start_bytes = (thread_kernel ? sizeof(Position) : sizeof(PaddedPosition)) * (size_t)S;
+    const size_t start_bytes = (thread_kernel ? sizeof(Position) : (group_lanes ? sizeof(GroupPosition) : sizeof(PaddedPosition))) * (size_t)S;
     if ((st = ensure(&d_starts_, &cap_starts_, start_bytes))) return st;
     if ((st = ensure(&d_descs_, &cap_descs_, sizeof(StartDesc) * (size_t)S))) return st;
     if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)S))) return st;
@@ -144,6 +152,9 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     }
     if (thread_kernel) {
         memcpy(h_stage_, starts.data(), start_bytes);
+    } else if (group_lanes) {
+        GroupPosition* gp = (GroupPosition*)h_stage_;
+        for (int i = 0; i < S; i++) to_group(starts[i], &gp[i]);
     } else {
         PaddedPosition* pp = (PaddedPosition*)h_stage_;
         for (int i = 0; i < S; i++) to_padded(starts[i], &pp[i]);
@@ -158,6 +169,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     memset(&a, 0, sizeof(a));
     a.starts = (const Position*)d_starts_;
     a.pstarts = (const PaddedPosition*)d_starts_;
+    a.gstarts = (const GroupPosition*)d_starts_;
     a.jump = (const JumpTable*)d_jump_;
     a.descs = (const StartDesc*)d_descs_;
     a.n_starts = S;
@@ -180,6 +192,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
         cudaError_t e;
         const int n = board.n();
         if (thread_kernel) e = launch_playout_thread(n, a, sm_count_, stream_, &info_);
+        else if (group_lanes) e = launch_playout_group(n, group_lanes, a, sm_count_, stream_, &info_);
         else e = launch_playout_warp(n, a, sm_count_, stream_, &info_);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     }

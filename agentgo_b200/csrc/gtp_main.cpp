@@ -2,7 +2,7 @@
 // self-play driver for BASELINE.json configs[3] (device-timed genmove latency).
 //
 //   agentgo_gtp [--boardsize N] [--playouts P] [--total-playouts M] [--root-playouts R]
-//               [--device D] [--gpus N] [--seed S] [--kernel auto|thread|warp]
+//               [--device D] [--gpus N] [--seed S] [--kernel auto|thread|warp|group8|group16|group32]
 //               [--amaf] [--static] [--book] [--reference-policy]
 //               [--selfplay [--max-moves K]]
 //               [--match G [--white-playouts P] [--white-policy flat|reference]]
@@ -66,7 +66,8 @@ int main(int argc, char** argv) {
         else if (a == "--white-policy") white_policy = std::string(next("--white-policy")) == "reference" ? 1 : 0;
         else if (a == "--kernel") {
             const std::string k = next("--kernel");
-            cfg.kernel = k == "thread" ? AGB_KERNEL_THREAD : (k == "warp" ? AGB_KERNEL_WARP : AGB_KERNEL_AUTO);
+            cfg.kernel = k == "thread" ? AGB_KERNEL_THREAD : (k == "warp" ? AGB_KERNEL_WARP : (k == "group8" ? AGB_KERNEL_GROUP8 :
+                         (k == "group16" ? AGB_KERNEL_GROUP16 : (k == "group32" ? AGB_KERNEL_GROUP32 : AGB_KERNEL_AUTO))));
         } else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     // --gpus N: one engine per GPU (devices device..device+N-1), shard i of N, one NCCL communicator

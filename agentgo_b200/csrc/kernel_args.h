@@ -38,6 +38,21 @@ struct PaddedPosition {
     int16_t n_el, stones, ko_key_col, ko_idx, last[2], ending, pad;
 };
 
+// Device layout of a start position for the group kernel (playout_group.cuh): ONE word per point of
+// the padded board,
+//   bits 0-8 A | bits 9-17 next | bits 18-28 F | bits 30-31 colour
+//        stone:  A = root of its string, next = next stone of the string (511 = end),
+//                F = pseudo-liberties at the root stone / the string's last stone at its SECOND stone
+//        empty:  A = the point itself, next = slot of the point in `elist`
+//        border: A = the point itself, colour 3
+// and the same append-only array of empty points as PaddedPosition.
+constexpr int group_elist_cap(int n) { return n * n + 15; }    // entries in shared memory; compacted when full
+struct GroupPosition {
+    uint32_t w[kMaxNP];
+    uint32_t elist_w[(kMaxNN + 1) / 2];    // n_el 16-bit entries
+    int16_t n_el, stones, ko_key_col, ko_idx, last[2], ending, pad;
+};
+
 // GF(2) jump-ahead table of TinyMT32: T^k split by state nibble (k = jump_steps(), the number of
 // draws each lane generates per ring refill).  e[l*16 + v] is the image of state nibble l (bits
 // 4l..4l+3 of s0|s1|s2|s3) having value v; the new state is the XOR of the 32 selected entries.
@@ -52,6 +67,7 @@ struct JumpTable {
 struct KernelArgs {
     const Position* starts;     // [n_starts] device (thread kernel)
     const PaddedPosition* pstarts;  // [n_starts] device (warp kernel)
+    const GroupPosition* gstarts;   // [n_starts] device (group kernel)
     const JumpTable* jump;      // device
     const StartDesc* descs;     // [n_starts] device
     int32_t n_starts;
@@ -76,8 +92,10 @@ struct LaunchInfo {
     const char* name;
 };
 
-// host helpers of the warp kernel's device layout (playout_warp.cu)
+// host helpers of the device layouts (host_layout.cpp)
 void to_padded(const Position& p, PaddedPosition* out);
+void to_group(const Position& p, GroupPosition* out);
+constexpr int kJumpSteps = 16;             // draws each lane generates per ring refill, both kernels
 int jump_steps();
 void build_jump(const RngParams& prm, int steps, JumpTable* out);
 // bounds violations counted by the AGB_CHECK_BOUNDS build of the warp kernel (0 in release)
@@ -89,6 +107,8 @@ unsigned long long debug_event(int which);
 cudaError_t launch_playout_thread(int n, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info);
 // warp-per-playout kernel (playout_warp.cu)
 cudaError_t launch_playout_warp(int n, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info);
+// several playouts per warp, `lanes` (8, 16 or 32) lanes each (playout_group.cu)
+cudaError_t launch_playout_group(int n, int lanes, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info);
 
 }  // namespace agb
 

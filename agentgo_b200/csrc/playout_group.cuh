@@ -1,0 +1,691 @@
+// playout_group.cuh — SEVERAL playouts per warp: a group of G lanes (8 or 16; 32 for reference) owns
+// one playout, 32/G playouts advance in lock step in one warp (sm_100a).
+//
+// Why: the warp-per-playout kernel (playout_warp.cu) issues on 80 % of the scheduler cycles, but
+// only 13 % of its lane slots do algorithmic work — the board update, the loop glue and the scalar
+// parts of the move selection keep one lane busy and 31 waiting.  Here
+// those sections are shared by 32/G playouts, and the predicates of the policy are evaluated ONE
+// LANE PER POINT (all four directions of a point in one lane, no warp collectives inside), so a
+// neighbourhood evaluation (8 cells) or a rejection round (G draws pairs) of 32/G playouts is one
+// pass over the warp.
+//
+// Rules of this file:
+//  * CONTROL FLOW IS WARP-UNIFORM.  Every loop bound and every branch around a collective is
+//    derived from a ballot / any over the whole warp; what differs between the playouts of a
+//    warp is DATA (predicates per group).  Every collective therefore runs with the full mask in
+//    converged code — no divergent collectives, none of the BSSY/BSYNC/WARPSYNC scaffolding the
+//    compiler had to put around the collectives of the warp kernel.  tests/csrc/simt_emu.h runs
+//    this very source on the CPU and aborts if any lane reaches a collective at another site.
+//  * RARE BULK WORK BORROWS THE WHOLE WARP.  Clone, scoring, complex mode
+//    (Board::getRandomPieceComplex) and the compaction of the empty-point array serve one group at
+//    a time with all 32 lanes (the board of any group of the warp is in reach of every lane).
+//  * One 32-bit word per point (the warp kernel had two), padded (N+2)^2 board:
+//        bits 0-8   A     stone: root of its string; empty / border point: its own index
+//        bits 9-17  next  stone: next stone of the string in SetNode::pieces order (511 = end);
+//                         empty point: its slot in the empty-point array `elist`
+//        bits 18-28 F     root stone: pseudo-liberties (SetNode::hp); SECOND stone of a string: the
+//                         string's last stone (the tail is needed only when strings are joined, the
+//                         root on every lookup, so the root keeps the field that is one AND away)
+//        bits 30-31 colour (0 empty, 1 black, 2 white, 3 border)
+//    With A = own index on empty and border points the root of "whatever is next to a point" is
+//    w & 511 with no case split, and equal roots mean the same string.
+//  * The empty-point list is the append-only array of the warp kernel (kernel_args.h), the rand()
+//    ring too, but smaller (R = 2*G*SEG entries), refilled whenever a phase is about to read past
+//    its end: state per playout 3.1 KB at 19x19, 72 playouts per SM.
+//
+// Restates Board.cpp:68-177 (put), :293-339 (killSetNode), :341-411 (getRandomPiece), :413-478
+// (getRandomPieceComplex), :480-755 (predicates), :910-925 (countScore) and the pair loops of
+// AgentGo.cpp:285-327 / :412-448, bit for bit (tests/test_emu_group.py, tests/test_gpu_parity.py).
+#ifndef AGB_PLAYOUT_GROUP_CUH_
+#define AGB_PLAYOUT_GROUP_CUH_
+
+#include "kernel_args.h"
+
+#ifdef AGB_EMU
+#define AGB_DEV inline
+#define AGB_NOINLINE __attribute__((noinline))
+#else
+#define AGB_DEV __device__ __forceinline__
+#define AGB_NOINLINE __device__ __noinline__
+#endif
+
+namespace agb {
+namespace grp {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kNilG = 511u;
+constexpr uint32_t kHpOne = 1u << 18;
+constexpr uint32_t kHpMask = 0x7ffu << 18;
+constexpr uint32_t kNextMask = 511u << 9;
+constexpr uint32_t kResFlag = 0x8000u;     // elist entry: point is reserved in the current complex-mode call
+
+AGB_DEV uint32_t fA(uint32_t w) { return w & 511u; }
+AGB_DEV uint32_t fNext(uint32_t w) { return (w >> 9) & 511u; }
+AGB_DEV uint32_t fHp(uint32_t w) { return (w >> 18) & 0x7ffu; }
+AGB_DEV uint32_t fCol(uint32_t w) { return w >> 30; }
+AGB_DEV bool isEmpty(uint32_t w) { return w < 0x40000000u; }
+AGB_DEV bool isStone(uint32_t w) { return (int32_t)(w + 0x40000000u) < 0; }
+
+template <int N_, int G_, int SEG_>
+struct GCfg {
+    static constexpr int N = N_, G = G_, SEG = SEG_;
+    static constexpr int W = N + 2, NP = W * W, NN = N * N, NG = 32 / G;
+    static constexpr int BATCH = G * SEG;           // draws per refill of one playout
+    static constexpr int R = 2 * BATCH;             // ring entries
+    static constexpr int E = group_elist_cap(N);    // elist entries (kernel_args.h)
+    // shared-memory words of one playout: ring | board | elist, a multiple of 4 (the ring is
+    // written with 128-bit stores)
+    static constexpr int oRing = 0, oBoard = R / 2, oElist = oBoard + NP;
+    static constexpr int words = ((oElist + E / 2 + 3) / 4) * 4;
+    static constexpr int warp_words = NG * words;
+    static constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
+};
+
+// v % M for a 15-bit value and a small constant M: one IMAD.HI and one IMAD
+template <uint32_t M>
+AGB_DEV uint32_t mod_small(uint32_t v) {
+    const uint32_t q = __umulhi(v, (uint32_t)((0x100000000ull + M - 1) / M));
+    return v - q * M;
+}
+
+// ---- the policy's predicates, one lane per point -------------------------------------------------
+// checkSuicide/Kill/Survive/Dying/Chase/TrueEye/Compete (Board.cpp:480-755) of the EMPTY on-board
+// point idx for `agent`, computed by one lane from the 4 + 4 words around it.
+//   reserve = true eye | suicide | ko            (complex mode: no checkDying, :425-427)
+//   bad     = reserve | dying                    (the filter of both sampling phases)
+enum { kEvAll = 0, kEvBad = 1, kEvRes = 2 };
+struct Ev {
+    bool kill, survive, chase, bad;     // kEvRes: bad = reserve
+};
+template <int W, int MODE>
+AGB_DEV Ev eval_point(const uint32_t* w, uint32_t agent, int idx, int ko_key) {
+    const uint32_t enemy = 3u - agent;
+    const uint32_t v0 = w[idx - W], v1 = w[idx - 1], v2 = w[idx + W], v3 = w[idx + 1];
+    const uint32_t r0 = fA(v0), r1 = fA(v1), r2 = fA(v2), r3 = fA(v3);
+    const int h0 = (int)fHp(w[r0]), h1 = (int)fHp(w[r1]), h2 = (int)fHp(w[r2]), h3 = (int)fHp(w[r3]);
+    const uint32_t c0 = fCol(v0), c1 = fCol(v1), c2 = fCol(v2), c3 = fCol(v3);
+    // a string seen from several directions counts once, less its multiplicity (minus_hp, :506-515)
+    const bool e01 = r0 == r1, e02 = r0 == r2, e03 = r0 == r3, e12 = r1 == r2, e13 = r1 == r3, e23 = r2 == r3;
+    const int l0 = h0 - 1 - e01 - e02 - e03, l1 = h1 - 1 - e01 - e12 - e13;
+    const int l2 = h2 - 1 - e02 - e12 - e23, l3 = h3 - 1 - e03 - e13 - e23;
+    const bool en0 = c0 == enemy, en1 = c1 == enemy, en2 = c2 == enemy, en3 = c3 == enemy;
+    const bool fr0 = c0 == agent, fr1 = c1 == agent, fr2 = c2 == agent, fr3 = c3 == agent;
+    const int n_empty = (c0 == 0) + (c1 == 0) + (c2 == 0) + (c3 == 0);
+    const bool ecap = (en0 && l0 == 0) || (en1 && l1 == 0) || (en2 && l2 == 0) || (en3 && l3 == 0);
+    const bool fsafe = (fr0 && l0 > 0) || (fr1 && l1 > 0) || (fr2 && l2 > 0) || (fr3 && l3 > 0);
+    const bool suicide = n_empty == 0 && !ecap && !fsafe;                       // :480-524
+    // Board::checkTrueEye, :735-751: a point is on the edge iff an orthogonal neighbour is border
+    const bool own4 = (fr0 || c0 == 3) && (fr1 || c1 == 3) && (fr2 || c2 == 3) && (fr3 || c3 == 3);
+    const bool edge = c0 == 3 || c1 == 3 || c2 == 3 || c3 == 3;
+    const int cnt = (fCol(w[idx - W - 1]) == enemy) + (fCol(w[idx - W + 1]) == enemy) +
+                    (fCol(w[idx + W - 1]) == enemy) + (fCol(w[idx + W + 1]) == enemy);
+    const bool eye = own4 && cnt < (edge ? 1 : 2);
+    const bool ko = ko_key == (int)((agent << 16) | (uint32_t)idx);             // :753-755
+    Ev e;
+    e.kill = e.survive = e.chase = false;
+    e.bad = eye || suicide || ko;
+    if (MODE == kEvRes) return e;
+    const bool f1 = !e01, f2 = !(e02 || e12), f3 = !(e03 || e13 || e23);        // first sight of the string
+    const int fsum = (fr0 ? l0 : 0) + (fr1 && f1 ? l1 : 0) + (fr2 && f2 ? l2 : 0) + (fr3 && f3 ? l3 : 0);
+    const int tot = n_empty + fsum;
+    e.bad = e.bad || (!ecap && tot == 1);                                       // checkDying, :628-679
+    if (MODE == kEvAll) {
+        const bool eatari = (en0 && l0 == 1) || (en1 && l1 == 1) || (en2 && l2 == 1) || (en3 && l3 == 1);
+        const bool fcap = (fr0 && l0 == 0) || (fr1 && l1 == 0) || (fr2 && l2 == 0) || (fr3 && l3 == 0);
+        const int fmin = min(min(fr0 ? h0 : 9999, fr1 ? h1 : 9999), min(fr2 ? h2 : 9999, fr3 ? h3 : 9999));
+        e.kill = ecap;                                                          // :526-563
+        e.survive = fcap && (ecap || tot > fmin);                               // :565-626
+        e.chase = eatari && tot > 1;                                            // :681-733
+    }
+    return e;
+}
+
+// ---- rand(): ring refill ------------------------------------------------------------------------
+// The next BATCH = G*SEG draws of the playouts that take part (`part`, a per-group predicate).  The
+// serial part is the G segment-start states: TinyMT32's transition is linear over GF(2), T^SEG is a
+// nibble table (JumpTable), every lane of the group looks up its 32/G nibbles and the group folds
+// them with redux.xor; each state is parked in the ring segment of the lane that will generate from
+// it.  Then every lane generates its SEG draws.  Groups that do not take part run along and store
+// nothing.
+struct GenState {
+    uint32_t g0, g1, g2, g3, gen_end;
+};
+template <class C>
+AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* __restrict__ tab,
+                             int gl, unsigned gmask) {
+    constexpr int NPL = 32 / C::G;                  // nibbles per lane
+    const int widx = (gl * NPL) >> 3;
+    const uint32_t sh0 = (uint32_t)((gl * NPL) & 7) * 4u;
+    const uint4* __restrict__ mytab = tab + gl * NPL * 16;
+    uint4* park = reinterpret_cast<uint4*>(ring + (st.gen_end & (uint32_t)(C::R - 1)));
+    uint32_t a0 = st.g0, a1 = st.g1, a2 = st.g2, a3 = st.g3;
+#pragma unroll 2
+    for (int l = 0; l < C::G; l++) {
+        if (part) park[(C::SEG / 8) * l] = make_uint4(a0, a1, a2, a3);
+        const uint32_t word = widx == 0 ? a0 : (widx == 1 ? a1 : (widx == 2 ? a2 : a3));
+        const uint32_t bits = word >> sh0;
+        uint4 t = __ldg(mytab + (bits & 15u));
+#pragma unroll
+        for (int n = 1; n < NPL; n++) {
+            const uint4 u = __ldg(mytab + n * 16 + ((bits >> (4 * n)) & 15u));
+            t.x ^= u.x; t.y ^= u.y; t.z ^= u.z; t.w ^= u.w;
+        }
+        a0 = __reduce_xor_sync(gmask, t.x);
+        a1 = __reduce_xor_sync(gmask, t.y);
+        a2 = __reduce_xor_sync(gmask, t.z);
+        a3 = __reduce_xor_sync(gmask, t.w);
+    }
+    __syncwarp();
+    TinyMT mine;
+    {
+        const uint4 s = park[(C::SEG / 8) * gl];
+        mine.s0 = s.x; mine.s1 = s.y; mine.s2 = s.z; mine.s3 = s.w;
+    }
+    __syncwarp();
+    uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
+#pragma unroll 2
+    for (int j = 0; j < C::SEG / 2; j++) {
+        mine.next_state(prm.mat1, prm.mat2);
+        const uint32_t lo = mine.temper(prm.tmat) >> 17;
+        mine.next_state(prm.mat1, prm.mat2);
+        const uint32_t hi = mine.temper(prm.tmat) >> 17;
+        if (part) out[j] = lo | (hi << 16);
+    }
+    __syncwarp();
+    if (part) { st.g0 = a0; st.g1 = a1; st.g2 = a2; st.g3 = a3; st.gen_end += (uint32_t)C::BATCH; }
+    return st;
+}
+
+// ---- bulk work, all 32 lanes for one group ------------------------------------------------------
+// Drop the dead entries of elist, keeping the order.  Entry k naming point c is alive iff c is
+// empty and its slot is k (a zeroed entry names the border point 0).  In place: a round reads 32
+// entries and then writes at or below where it read.  Returns the new number of entries.
+template <class C>
+AGB_NOINLINE int compact(uint32_t* w, uint16_t* elist, int n_el, int lane) {
+    int out = 0;
+#pragma unroll 1
+    for (int base = 0; base < n_el; base += 32) {
+        const int k = base + lane;
+        const uint32_t c = k < n_el ? ((uint32_t)elist[k] & 0x1ffu) : 0u;
+        const uint32_t wc = w[c];
+        const bool alive = isEmpty(wc) && (int)fNext(wc) == k;
+        const unsigned m = __ballot_sync(kFull, alive);
+        __syncwarp();
+        if (alive) {
+            const int o = out + __popc(m & ((1u << lane) - 1u));
+            elist[o] = (uint16_t)c;
+            w[c] = c | ((uint32_t)o << 9);
+        }
+        out += __popc(m);
+    }
+    __syncwarp();
+    return out;
+}
+
+// Board::getRandomPieceComplex, Board.cpp:413-478, for one group.  Pass 1 (reserve flags, :419-433):
+// one lane per entry of elist, flagged in place.  Pass 2 (:445-470, the rnd-th unreserved point in
+// list order) counts 32 entries per round from the end of the array.  draw = the playout's next
+// rand() value; *used says whether it was consumed.
+template <class C>
+AGB_NOINLINE int complex_pick(uint32_t* w, uint16_t* elist, int n_el, int spaces, uint32_t agent, int ko_key,
+                              uint32_t draw, int lane, int* used) {
+    int reserved_total = 0;
+#pragma unroll 1
+    for (int base = 0; base < n_el; base += 32) {
+        const int k = base + lane;
+        const int ent = k < n_el ? (int)((uint32_t)elist[k] & 0x1ffu) : 0;          // 0: a dead entry
+        // dead entries look at some point of the board; their result is dropped
+        const Ev e = eval_point<C::W, kEvRes>(w, agent, ent ? ent : C::W + 1, ko_key);
+        const bool res = e.bad && ent != 0;
+        if (ent) elist[k] = (uint16_t)((uint32_t)ent | (res ? kResFlag : 0u));      // addReserve, :757-761
+        reserved_total += __popc(__ballot_sync(kFull, res));
+    }
+    __syncwarp();
+    const int range = spaces - reserved_total;
+    int pick = -1;
+    *used = 0;
+    if (range != 0) {
+        int rnd = (int)(draw % (uint32_t)range);
+        *used = 1;
+#pragma unroll 1
+        for (int top = n_el - 1; top >= 0; top -= 32) {
+            const int k = top - lane;                                               // lane order = list order
+            const uint32_t ent = k >= 0 ? (uint32_t)elist[k] : 0u;
+            const bool ok = ent - 1u < 0x7fffu;                                     // alive and not reserved
+            const unsigned m = __ballot_sync(kFull, ok);
+            const int c = __popc(m);
+            if (rnd < c) {
+                const bool hit = ok && __popc(m & ((1u << lane) - 1u)) == rnd;
+                pick = (int)__shfl_sync(kFull, ent, __ffs(__ballot_sync(kFull, hit)) - 1);
+                break;
+            }
+            rnd -= c;
+        }
+    }
+    return pick;
+}
+
+// Board::countScore(agent) - countScore(enemy), Board.cpp:910-925: an empty point counts for the
+// colour of its LEFT neighbour (right one in column 0)
+template <class C>
+AGB_DEV int score_diff(const uint32_t* w, uint32_t agent, int lane) {
+    int d = 0;
+#pragma unroll 1
+    for (int idx = C::W + lane; idx < C::NP - C::W; idx += 32) {
+        const uint32_t c = fCol(w[idx]);
+        if (c == 3) continue;
+        uint32_t owner = c;
+        if (c == 0) {
+            const uint32_t l = fCol(w[idx - 1]);
+            owner = l != 3 ? l : fCol(w[idx + 1]);
+        }
+        d += (int)(owner == agent) - (int)(owner == 3u - agent);
+    }
+    return (int)__reduce_add_sync(kFull, (unsigned)d);
+}
+
+// ---- the kernel body ----------------------------------------------------------------------------
+template <class C>
+AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int lane) {
+    constexpr int G = C::G, W = C::W;
+    constexpr uint32_t RM = (uint32_t)(C::R - 1);
+    const int gl = lane & (G - 1);
+    const int gbase = lane & ~(G - 1);
+    const int grp = lane / G;
+    const unsigned gmask = C::GM << gbase;
+    uint32_t* const gsm = smem_warp + grp * C::words;
+    uint16_t* const ring = reinterpret_cast<uint16_t*>(gsm + C::oRing);
+    uint32_t* const w = gsm + C::oBoard;
+    uint16_t* const elist = reinterpret_cast<uint16_t*>(gsm + C::oElist);
+    const uint4* __restrict__ jt = a.jump->e;
+
+    // lane constants: direction of the stone update (lanes 4k..4k+3 = up, left, down, right) and
+    // cell of the 3x3 block around the opponent's last move (centre skipped)
+    const int dir = lane & 3;
+    const int off_nb = dir == 0 ? -W : (dir == 1 ? -1 : (dir == 2 ? W : 1));
+    const int c8 = gl & 7;
+    const int cc = c8 + (c8 >= 4);
+    const int off_cell = (cc / 3 - 1) * W + (cc % 3 - 1);
+    const unsigned qmask = 15u << (lane & ~3);
+    const int qbase = lane & ~3;
+
+    // state of this lane's playout, the same in all G lanes of the group
+    enum { kFetch = 0, kPlay = 1, kEnded = 2, kDone = 3 };
+    int phase = kFetch;
+    uint32_t colour = 1, first = 1;
+    int prev = -1, stones = 0, ko_key = -1, ending = 0, n_el = 0, n_dead = -1;
+    uint32_t pos = 0, mv = 0;
+    GenState gs = {0, 0, 0, 0, 0};
+    int s_idx = 0;
+    long long gid = 0;
+    bool fault = false;
+
+#pragma unroll 1
+    for (;;) {
+        // ---- service: score the playouts that ended, hand out new ones (all 32 lanes per group) ----
+        unsigned need = __ballot_sync(kFull, phase == kFetch || phase == kEnded);
+#pragma unroll 1
+        while (need) {
+            const int X = (__ffs(need) - 1) / G;
+            const int src = X * G;
+            need &= ~(C::GM << src);
+            uint32_t* const xsm = smem_warp + X * C::words;
+            uint32_t* const xw = xsm + C::oBoard;
+            if (__shfl_sync(kFull, phase, src) == kEnded) {
+                const int xs = __shfl_sync(kFull, s_idx, src);
+                const long long xg = __shfl_sync(kFull, gid, src);
+                const uint32_t xmv = __shfl_sync(kFull, mv, src);
+                const uint32_t xpos = __shfl_sync(kFull, pos, src);
+                const bool xfault = __shfl_sync(kFull, (int)fault, src) != 0;
+                const StartDesc d = a.descs[xs];
+                const int diff = xfault ? -32768 : score_diff<C>(xw, (uint32_t)d.agent, lane);
+                if (lane == 0) {
+                    atomicAdd(&a.stats[kStatMoves], (unsigned long long)xmv);
+                    atomicAdd(&a.stats[kStatDraws], (unsigned long long)xpos);
+                    atomicAdd(&a.stats[kStatPlayouts], 1ull);
+                    if (xfault) atomicAdd(&a.stats[kStatFaults], 1ull);
+                    if (a.diffs) a.diffs[xg] = (int16_t)diff;
+                    if (!xfault) {
+                        const int wr = diff - d.avrg_win;                        // AgentGo.cpp:327
+                        unsigned long long* c = (unsigned long long*)a.counters;
+                        if (wr >= 0) {                                           // sign test of AgentGo.cpp:328
+                            atomicAdd(&c[xs], 1ull);
+                            atomicAdd(&c[a.n_starts + xs], (unsigned long long)wr);
+                        } else {
+                            atomicAdd(&c[2 * a.n_starts + xs], (unsigned long long)(long long)wr);
+                        }
+                    }
+                }
+            }
+            unsigned long long l = 0;
+            if (lane == 0) l = atomicAdd(a.work_counter, 1ull);
+            l = __shfl_sync(kFull, l, 0);
+            const bool has = l < (unsigned long long)a.local_units;
+            if (has) {
+                const long long g = (long long)l * a.shard_count + a.shard_rank;
+                const int s = (int)(g / a.P);
+                const long long p = g - (long long)s * a.P;
+                const GroupPosition& gp = a.gstarts[s];
+                const StartDesc d = a.descs[s];
+                __syncwarp();
+#pragma unroll 1
+                for (int i = lane; i < C::NP; i += 32) xw[i] = gp.w[i];          // Board::clone, Board.cpp:216-254
+                {
+                    uint32_t* xe = xsm + C::oElist;
+#pragma unroll 1
+                    for (int i = lane; i < (C::NN + 1) / 2; i += 32) xe[i] = gp.elist_w[i];
+                }
+                __syncwarp();
+                int lm = gp.last[2 - d.first];                                   // last_move[enemy of the first mover]
+                // Board.cpp:356 for the first move: the opponent's last stone may have been captured since
+                if (lm >= 0 && fCol(xw[lm]) != 3u - (uint32_t)d.first) lm = -1;
+                // tinymt32_init (RFC 8682)
+                TinyMT t;
+                t.init(playout_seed(a.seed_base, d.position_id, d.cand_idx, (uint64_t)p), a.rng.mat1, a.rng.mat2, a.rng.tmat);
+                if (grp == X) {
+                    phase = kPlay;
+                    colour = first = (uint32_t)d.first;
+                    prev = lm;
+                    stones = gp.stones;
+                    ko_key = gp.ko_key_col > 0 ? ((gp.ko_key_col << 16) | gp.ko_idx) : -1;
+                    ending = gp.ending;
+                    n_el = gp.n_el;
+                    n_dead = -1;
+                    pos = 0; mv = 0;
+                    gs.g0 = t.s0; gs.g1 = t.s1; gs.g2 = t.s2; gs.g3 = t.s3; gs.gen_end = 0;
+                    s_idx = s; gid = g; fault = false;
+                }
+            } else if (grp == X) {
+                phase = kDone;
+            }
+        }
+        if (!__any_sync(kFull, phase == kPlay)) break;
+        const bool live = phase == kPlay;
+
+#define AGB_ENSURE(needpred, k)                                                                     \
+        if (__any_sync(kFull, (needpred) && gs.gen_end - pos < (uint32_t)(k))) {                     \
+            const bool part_ = live && gs.gen_end - pos <= (uint32_t)(C::R - C::BATCH);              \
+            gs = refill<C>(part_, ring, gs, a.rng, jt, gl, gmask);                                   \
+        }
+
+        // ---- Board::getRandomPiece, Board.cpp:341-411 ----
+        bool cplx = false;
+        if (ending) {                                                           // :348-351
+            if (stones <= kEndingStones) ending = 0;
+            else cplx = true;
+        }
+        const bool search = live && !cplx;
+        if (search) n_dead = -1;                                                // put stops maintaining elist
+        int r = -1;
+        bool found = false;
+        // neighbourhood phase, :354-380: the 8 cells around the opponent's last move, one lane each.
+        // (:356 also wants that stone to be still there; inside a playout it always is, and for the
+        // first move of a playout that was settled when it was set up.)
+        const bool nbact = search && prev >= 0;
+        if (__any_sync(kFull, nbact)) {
+            AGB_ENSURE(nbact, 18)
+            const int cidx0 = nbact ? prev + off_cell : W + 1;
+            const bool onb = nbact && isEmpty(w[cidx0]);                        // empty => on the board
+            const int cidx = onb ? cidx0 : W + 1;
+            const Ev e = eval_point<W, kEvAll>(w, colour, cidx, ko_key);
+            const bool ok = onb && !e.bad && (G == 8 || gl < 8);
+            uint32_t bits = (ok && e.kill ? 1u << c8 : 0u) | (ok && e.survive ? 0x100u << c8 : 0u) |
+                            (ok && e.chase ? 0x10000u << c8 : 0u);
+            bits = __reduce_or_sync(gmask, bits);
+            if (__any_sync(kFull, bits != 0)) {
+                // iteration k of `for (k = 0; k < 9; k++)` consumes draws 2k, 2k+1; lane k looks at it
+                // (G == 8: the ninth iteration is looked at by every lane of the group)
+                const unsigned K = bits & 0xffu, S = (bits >> 8) & 0xffu, Cm = bits >> 16;
+                bool hit; int pt;
+                {
+                    const uint32_t ra = mod_small<3>(ring[(pos + 2u * gl) & RM]);
+                    const uint32_t rb = mod_small<3>(ring[(pos + 2u * gl + 1u) & RM]);
+                    const uint32_t c9 = ra * 3u + rb;
+                    const uint32_t cx = c9 - (c9 > 4u);
+                    const unsigned m = K | (gl < 6 ? S : 0u) | (gl < 4 ? Cm : 0u);
+                    hit = gl < 9 && c9 != 4u && ((m >> cx) & 1u);               // the centre is occupied
+                    pt = prev + (int)(ra * W + rb) - (W + 1);
+                }
+                unsigned hm = (__ballot_sync(kFull, hit) >> gbase) & C::GM;
+                int pt8 = -1;
+                if (G == 8) {
+                    const uint32_t ra = mod_small<3>(ring[(pos + 16u) & RM]);
+                    const uint32_t rb = mod_small<3>(ring[(pos + 17u) & RM]);
+                    const uint32_t c9 = ra * 3u + rb;
+                    const uint32_t cx = c9 - (c9 > 4u);
+                    if (c9 != 4u && ((K >> cx) & 1u)) hm |= 0x100u;
+                    pt8 = prev + (int)(ra * W + rb) - (W + 1);
+                }
+                const int k = __ffs(hm) - 1;
+                const int ptk = __shfl_sync(kFull, pt, gbase + (k & (G - 1)));
+                if (nbact && hm) {
+                    pos += 2u * (uint32_t)(k + 1);
+                    r = (G == 8 && k == 8) ? pt8 : ptk;
+                    found = true;
+                }
+            }
+            if (nbact && !found) pos += 18;     // nine iterations, two draws each, none accepted
+        }
+        // rejection loop, :382-406: G pairs per round, lane j looks at pair j.  lim = the pairs that
+        // may still be accepted: the 100th draw is consumed but never accepted (:402-405)
+        {
+            int lim = kEndingThreshold - 1;
+            bool rej = search && !found;
+#pragma unroll 1
+            while (__any_sync(kFull, rej)) {
+                AGB_ENSURE(rej, 2 * G)
+                const uint32_t row = mod_small<C::N>(ring[(pos + 2u * gl) & RM]);
+                const uint32_t cl = mod_small<C::N>(ring[(pos + 2u * gl + 1u) & RM]);
+                const int idx = (int)(row * W + cl) + (W + 1);
+                const bool can = rej && gl < lim && isEmpty(w[idx]);
+                const Ev e = eval_point<W, kEvBad>(w, colour, idx, ko_key);
+                const unsigned good = (__ballot_sync(kFull, can && !e.bad) >> gbase) & C::GM;
+                const int k = __ffs(good) - 1;
+                const int ptk = __shfl_sync(kFull, idx, gbase + (k & (G - 1)));
+                if (rej) {
+                    if (good) {
+                        r = ptk; found = true; rej = false;
+                        pos += 2u * (uint32_t)(k + 1);
+                    } else {
+                        const int B = min(G, lim + 1);                          // pairs consumed by this round
+                        pos += 2u * (uint32_t)B;
+                        lim -= B;
+                        if (lim < 0) { ending = 1; cplx = true; rej = false; }
+                    }
+                }
+            }
+        }
+        // complex mode, :413-478: all 32 lanes for one group at a time
+        {
+            unsigned cm = __ballot_sync(kFull, live && cplx);
+            if (cm) {
+                AGB_ENSURE(cplx, 1)
+#pragma unroll 1
+                while (cm) {
+                    const int X = (__ffs(cm) - 1) / G;
+                    const int src = X * G;
+                    cm &= ~(C::GM << src);
+                    uint32_t* const xsm = smem_warp + X * C::words;
+                    uint32_t* const xw = xsm + C::oBoard;
+                    uint16_t* const xel = reinterpret_cast<uint16_t*>(xsm + C::oElist);
+                    int xn = __shfl_sync(kFull, n_el, src);
+                    int xd = __shfl_sync(kFull, n_dead, src);
+                    const int xstones = __shfl_sync(kFull, stones, src);
+                    const int xko = __shfl_sync(kFull, ko_key, src);
+                    const uint32_t xcol = __shfl_sync(kFull, colour, src);
+                    const uint32_t xpos = __shfl_sync(kFull, pos, src);
+                    const int spaces = C::NN - xstones;
+                    int pick = -1, used = 0;
+                    if (spaces != 0) {
+                        // Complex mode is sticky (game_ending, :348-351): the array is made dense once
+                        // and then kept current by put (zeroes the entry) and the captures (append).
+                        if (xd < 0 || xd >= 8) { xn = compact<C>(xw, xel, xn, lane); xd = 0; }
+                        const uint32_t draw = reinterpret_cast<const uint16_t*>(xsm + C::oRing)[xpos & RM];
+                        pick = complex_pick<C>(xw, xel, xn, spaces, xcol, xko, draw, lane, &used);
+                    }
+                    if (grp == X) { r = pick; n_el = xn; n_dead = xd; pos += (uint32_t)used; }
+                }
+            }
+        }
+
+        // ---- Board::put, Board.cpp:68-177, or Board::pass, :200-203 ----
+        const bool doput = live && r >= 0;
+        if (live) ko_key = -1;
+        if (__any_sync(kFull, doput)) {
+            const int idx = doput ? r : W + 1;
+            if (doput) { stones++; mv++; }
+            // Nothing is unlinked from the empty list: the entry of the point dies by itself; only
+            // while complex mode lasts it is zeroed, so that the array has no stale entries.
+            {
+                const bool maint = doput && n_dead >= 0;
+                if (__any_sync(kFull, maint)) {
+                    if (maint) {
+                        if (gl == 0) elist[fNext(w[idx])] = 0;
+                        n_dead++;
+                    }
+                    __syncwarp();
+                }
+            }
+            // lane d (mod 4) looks at neighbour d (up, left, down, right): colour, string, liberties
+            const uint32_t v = w[idx + off_nb];
+            const uint32_t root = fA(v);
+            const uint32_t rw = w[root];
+            const uint32_t col = fCol(v);
+            const bool enemy = doput && col == 3u - colour, frnd = doput && col == colour;
+            const unsigned same = __match_any_sync(kFull, root) & qmask;       // directions seeing the same string
+            const int mult = __popc(same);
+            const bool firstl = (same & ((1u << lane) - 1u)) == 0;
+            const bool lastl = (same >> lane) == 1u;
+            const int left = (int)fHp(rw) - mult;
+            const int hp_self = __popc(__ballot_sync(kFull, col == 0) & qmask);               // own liberties, :123-127
+            // captured strings, named by the LAST direction that sees them: that is when the reference
+            // finds their liberties gone (:129-164), so this is the order in which they leave the board
+            unsigned caps = (__ballot_sync(kFull, enemy && left == 0 && lastl) >> qbase) & 15u;
+            const unsigned frq = (__ballot_sync(kFull, frnd && firstl) >> qbase) & 15u;        // distinct own strings
+            const bool act = (G == 4) || gl < 4;                               // one quad of the group does the stores
+            // enemy strings lose one liberty per adjacency (sn->hp -= 1, :130,:138,:146,:154)
+            if (act && enemy && firstl) w[root] = rw - (uint32_t)mult * kHpOne;
+            // Own strings: everything the four sequential neighbour steps of :129-167 do commutes except
+            // the unions, whose net effect is known in closed form.  With F1..Fk the distinct own
+            // strings in direction order the reference ends with root Fk, piece order Fk, ..., F1, new
+            // stone (each union appends the mover's current string to the neighbour's,
+            // SetNode.cpp:78-82), hp = sum(hp_i - mult_i) + own.  The liberties a capture gives back
+            // are added afterwards (they commute with all of this).
+            uint32_t fk = (uint32_t)idx;
+            int hp_total = hp_self;
+            if (__any_sync(kFull, frq != 0)) {
+                const int top = frq ? 31 - __clz(frq) : 0;
+                const uint32_t fk_ = __shfl_sync(kFull, root, qbase + top);
+                if (frq) fk = fk_;
+                int t = (frnd && firstl) ? left : 0;
+                t += __shfl_xor_sync(kFull, t, 1);
+                t += __shfl_xor_sync(kFull, t, 2);
+                hp_total += t;
+                // the last stone of this lane's string: the root itself, or what its second stone says
+                const uint32_t nx = fNext(rw);
+                const uint32_t sw = w[nx != kNilG ? nx : root];
+                const uint32_t tail = nx != kNilG ? fHp(sw) : root;
+                // lane of F_i links its tail to the head of F_(i-1), the lane of F_1 to the new stone
+                const unsigned lower = frq & ((1u << dir) - 1u);
+                const uint32_t below = __shfl_sync(kFull, root, qbase + (lower ? 31 - __clz(lower) : 0));
+                const uint32_t target = lower ? below : (uint32_t)idx;
+                const bool own = act && frnd && firstl;
+                if (own) {
+                    const uint32_t tw = w[tail];
+                    w[tail] = (tw & ~kNextMask) | (target << 9);
+                }
+                // strings F_1..F_(k-1) are relabelled to Fk (:284-289), each by its own lane
+                bool walk = own && root != fk;
+                uint32_t cur = root;
+#pragma unroll 1
+                while (__any_sync(kFull, walk)) {
+                    if (walk) {
+                        const uint32_t cw = w[cur];
+                        w[cur] = (cw & ~511u) | fk;
+                        walk = cur != tail;
+                        cur = fNext(cw);
+                    }
+                }
+                __syncwarp();
+                if (own && root == fk) {
+                    const uint32_t rw2 = w[fk];
+                    w[fk] = (rw2 & ~kHpMask) | ((uint32_t)hp_total << 18);
+                    // the new stone is the last one; the second stone of Fk says so
+                    const uint32_t sec = nx != kNilG ? nx : target;
+                    if (sec != (uint32_t)idx) {
+                        const uint32_t x = w[sec];
+                        w[sec] = (x & ~kHpMask) | ((uint32_t)idx << 18);
+                    }
+                }
+            }
+            // SetNode::init (SetNode.cpp:31-44) for a stone on its own, else the last stone of Fk
+            if (doput && gl == 0)
+                w[idx] = fk | (kNilG << 9) | ((frq ? (uint32_t)idx : (uint32_t)hp_self) << 18) | (colour << 30);
+            __syncwarp();
+            // Board::killSetNode, :293-339: one captured stone per group and step; lanes 0..3 of the
+            // group give the liberty back to the strings around it (increments commute: atomics)
+            if (__any_sync(kFull, caps != 0)) {
+                uint32_t kcur = kNilG;
+                bool single = false;
+#pragma unroll 1
+                for (;;) {
+                    const int dcap = caps ? __ffs(caps) - 1 : 0;
+                    const uint32_t victim = __shfl_sync(kFull, root, qbase + dcap);
+                    if (kcur == kNilG && caps) {
+                        caps &= caps - 1u;
+                        kcur = victim;
+                        single = fNext(w[victim]) == kNilG;
+                    }
+                    if (!__any_sync(kFull, kcur != kNilG)) break;
+                    // the array is full: drop its stale entries (all 32 lanes per group)
+                    unsigned full = __ballot_sync(kFull, kcur != kNilG && n_el == C::E);
+#pragma unroll 1
+                    while (full) {
+                        const int X = (__ffs(full) - 1) / G;
+                        const int src = X * G;
+                        full &= ~(C::GM << src);
+                        uint32_t* const xsm = smem_warp + X * C::words;
+                        const int xn = compact<C>(xsm + C::oBoard, reinterpret_cast<uint16_t*>(xsm + C::oElist),
+                                                  __shfl_sync(kFull, n_el, src), lane);
+                        if (grp == X) { n_el = xn; if (n_dead > 0) n_dead = 0; }
+                    }
+                    // (the group's first lane rewrites the stone's word below: the link is read by it
+                    // alone, before that, and handed to the others)
+                    const uint32_t nxk = __shfl_sync(kFull, fNext(w[kcur != kNilG ? kcur : 0]), gbase);
+                    if (kcur != kNilG) {
+                        const uint32_t vn = w[(int)kcur + off_nb];                   // one liberty back, :323-326
+                        if (act && fCol(vn) == colour) atomicAdd(&w[fA(vn)], kHpOne);
+                        stones--;
+                        if (gl == 0) {
+                            elist[n_el] = (uint16_t)kcur;                       // push at the list head, :311-321
+                            w[kcur] = kcur | ((uint32_t)n_el << 9);             // empty, slot = n_el
+                        }
+                        n_el++;
+                        if (single) ko_key = (int)(((3u - colour) << 16) | kcur);   // :328-333
+                        kcur = nxk;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+
+        // ---- pair loop of MyWorker::work (AgentGo.cpp:295-325) / testAvrgWin (:422-443) ----
+        // The move that closes a pair (the second mover's) ends the playout when neither side moved:
+        // the first mover's move is what prev still holds, -1 for a pass.
+        if (live) {
+            const int before = prev;
+            prev = r;                                                           // Board.cpp:171 / :202
+            if (colour != first) {
+                if ((before & r) < 0) phase = kEnded;
+                else if ((int)mv > a.max_moves) { fault = true; phase = kEnded; }   // fault detector, once per pair
+            }
+            colour = 3u - colour;
+        }
+#undef AGB_ENSURE
+    }
+}
+
+}  // namespace grp
+}  // namespace agb
+
+#endif  // AGB_PLAYOUT_GROUP_CUH_

@@ -84,7 +84,10 @@ typedef enum agb_status {
 typedef enum agb_kernel {
     AGB_KERNEL_AUTO = 0,
     AGB_KERNEL_THREAD = 1,  /* one thread per playout */
-    AGB_KERNEL_WARP = 2     /* one warp per playout   */
+    AGB_KERNEL_WARP = 2,    /* one warp per playout   */
+    AGB_KERNEL_GROUP8 = 3,  /* four playouts per warp, 8 lanes each  */
+    AGB_KERNEL_GROUP16 = 4, /* two playouts per warp, 16 lanes each  */
+    AGB_KERNEL_GROUP32 = 5  /* the group kernel's code with one playout per warp (comparison) */
 } agb_kernel;
 
 typedef struct agb_config {

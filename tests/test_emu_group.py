@@ -1,0 +1,68 @@
+"""The group kernel's device code (agentgo_b200/csrc/playout_group.cuh: 32/G playouts per warp, G
+lanes each) compiled for the CPU on the test-only warp emulator (tests/csrc/simt_emu.h) and compared
+with the golden vectors generated from the reference.  The emulator also enforces the property the
+kernel is built on: every warp collective is reached by all 32 lanes at the same call site.
+This is NOT a product path: the library has no CPU fallback."""
+import os
+
+import numpy as np
+import pytest
+
+from util import emu_group, emu_playouts, golden, split_moves
+
+
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_root_mode_golden(lanes):
+    emu = emu_group()
+    for n, P in ((9, 192), (13, 96), (19, 64)):
+        g = golden("root_%d.npz" % n)
+        o, d, s, _ = emu_playouts(emu, n, lanes, [], 1, None, P, seed_base=int(g["seed_base"]))
+        assert (d == g["diffs"][:P]).all()
+        assert s[3] == P and s[2] == 0
+
+
+@pytest.mark.parametrize("lanes", [8, 16])
+def test_candidates_golden(lanes):
+    emu = emu_group()
+    g = golden("cands_13_midgame.npz")
+    for ci in range(0, len(g["cands"]), 5):
+        c = tuple(int(x) for x in g["cands"][ci])
+        o, d, s, _ = emu_playouts(emu, 13, lanes, g["moves"], int(g["colour"]), c, int(g["P"]), avrg_win=int(g["avrg_win"]),
+                                  seed_base=int(g["seed_base"]), position_id=int(g["position_id"]), cand_idx=ci)
+        assert (d == g["diffs"][ci]).all()
+        assert (o[0], o[1], o[2]) == (g["wins"][ci], g["sum_pos"][ci], g["sum_neg"][ci])
+
+
+def test_midgame_golden():
+    emu = emu_group()
+    g = golden("midgame_19.npz")
+    moves = split_moves(g)
+    for bi in range(0, len(moves), 3):
+        P = 48
+        o, d, s, _ = emu_playouts(emu, 19, 8, moves[bi], int(g["to_move"][bi]), None, P, seed_base=int(g["seed_base"]),
+                                  position_id=int(g["position_ids"][bi]))
+        assert (d == g["diffs"][bi][:P]).all()
+
+
+def test_lane_order_does_not_matter():
+    """EMU_SHUFFLE runs the lanes of the emulated warp in a random order between two collectives: a
+    shared-memory hand-over between lanes without a __syncwarp() would change results."""
+    emu = emu_group()
+    g = golden("root_19.npz")
+    old = os.environ.get("EMU_SHUFFLE")
+    try:
+        for seed in ("5", "6"):
+            os.environ["EMU_SHUFFLE"] = seed
+            o, d, s, _ = emu_playouts(emu, 19, 8, [], 1, None, 32, seed_base=int(g["seed_base"]))
+            assert (d == g["diffs"][:32]).all()
+    finally:
+        if old is None:
+            os.environ.pop("EMU_SHUFFLE", None)
+        else:
+            os.environ["EMU_SHUFFLE"] = old
+
+
+def test_move_cap_is_a_fault():
+    emu = emu_group()
+    o, d, s, _ = emu_playouts(emu, 9, 8, [], 1, None, 8, max_moves=10)
+    assert s[2] == 8 and (d == -32768).all() and o.sum() == 0

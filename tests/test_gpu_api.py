@@ -8,7 +8,7 @@ from util import golden, split_moves
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [ag.KERNEL_THREAD, ag.KERNEL_WARP]
+KERNELS = [ag.KERNEL_THREAD, ag.KERNEL_WARP, ag.KERNEL_GROUP8, ag.KERNEL_GROUP16, ag.KERNEL_GROUP32]
 
 
 @pytest.mark.parametrize("kernel", KERNELS)

@@ -7,7 +7,7 @@ from oracle import pyoracle as po
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = [ag.KERNEL_THREAD, ag.KERNEL_WARP]
+KERNELS = [ag.KERNEL_THREAD, ag.KERNEL_WARP, ag.KERNEL_GROUP8, ag.KERNEL_GROUP16, ag.KERNEL_GROUP32]
 
 
 def oracle_board(n, moves=()):
