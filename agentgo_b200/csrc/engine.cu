@@ -92,7 +92,7 @@ Engine::~Engine() {
     cudaSetDevice(cfg.device);
     if (stream_) cudaStreamSynchronize(stream_);
     cudaFree(d_starts_); cudaFree(d_descs_); cudaFree(d_counters_); cudaFree(d_diffs_);
-    cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_amaf_);
+    cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_amaf_);
     if (h_pinned_) cudaFreeHost(h_pinned_);
     if (h_stage_) cudaFreeHost(h_stage_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -171,6 +171,18 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     a.pstarts = (const PaddedPosition*)d_starts_;
     a.gstarts = (const GroupPosition*)d_starts_;
     a.jump = (const JumpTable*)d_jump_;
+    if (group_lanes) {
+        // the per-lane jump matrices of the group kernel, built on first use for this lane count
+        if (jump_bytes_lanes_ != group_lanes) {
+            std::vector<uint4> jb(jump_bytes_size(group_lanes) / sizeof(uint4));
+            RngParams prm = {cfg.mat1, cfg.mat2, cfg.tmat};
+            build_jump_bytes(prm, group_lanes, kJumpSteps, jb.data());
+            if ((st = ensure(&d_jump_bytes_, &cap_jump_bytes_, jump_bytes_size(group_lanes)))) return st;
+            AGB_CUDA(cudaMemcpy(d_jump_bytes_, jb.data(), jump_bytes_size(group_lanes), cudaMemcpyHostToDevice));
+            jump_bytes_lanes_ = group_lanes;
+        }
+        a.jump_bytes = (const uint4*)d_jump_bytes_;
+    }
     a.descs = (const StartDesc*)d_descs_;
     a.n_starts = S;
     a.P = P;

@@ -69,6 +69,8 @@ private:
     cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
     void* d_starts_ = nullptr; size_t cap_starts_ = 0;
     void* d_jump_ = nullptr;             // JumpTable (TinyMT32 T^16), built at create time
+    void* d_jump_bytes_ = nullptr; size_t cap_jump_bytes_ = 0;   // JumpBytes of the group kernel
+    int jump_bytes_lanes_ = 0;           // lanes per playout d_jump_bytes_ was built for
     void* h_stage_ = nullptr; size_t cap_stage_ = 0;   // pinned staging of the start positions + descriptors
     void* d_descs_ = nullptr; size_t cap_descs_ = 0;
     void* d_counters_ = nullptr; size_t cap_counters_ = 0;

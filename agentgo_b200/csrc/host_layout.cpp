@@ -117,4 +117,27 @@ void build_jump(const RngParams& prm, int steps, JumpTable* out) {
         }
 }
 
+// The per-lane matrices of the group kernel (JumpBytes): lane 0 gets T^(lanes*seg), lane j T^(seg*j).
+void build_jump_bytes(const RngParams& prm, int lanes, int seg, uint4* out) {
+    for (int j = 0; j < lanes; j++) {
+        const int steps = j == 0 ? lanes * seg : seg * j;
+        uint32_t col[128][4];
+        for (int b = 0; b < 128; b++) {
+            TinyMT t;
+            t.s0 = t.s1 = t.s2 = t.s3 = 0;
+            (b < 32 ? t.s0 : (b < 64 ? t.s1 : (b < 96 ? t.s2 : t.s3))) = 1u << (b & 31);
+            for (int i = 0; i < steps; i++) t.next_state(prm.mat1, prm.mat2);
+            col[b][0] = t.s0; col[b][1] = t.s1; col[b][2] = t.s2; col[b][3] = t.s3;
+        }
+        for (int by = 0; by < 16; by++)
+            for (int v = 0; v < 256; v++) {
+                uint32_t acc[4] = {0, 0, 0, 0};
+                for (int k = 0; k < 8; k++)
+                    if (v & (1 << k))
+                        for (int wd = 0; wd < 4; wd++) acc[wd] ^= col[8 * by + k][wd];
+                out[((size_t)j * 16 + by) * 256 + v] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            }
+    }
+}
+
 }  // namespace agb

@@ -60,6 +60,18 @@ struct JumpTable {
     uint4 e[32 * 16];
 };
 
+// Jump tables of the group kernel: lane j of a playout's G lanes computes by itself, from the
+// generator state S at draw number gen_end, the state its own SEG-draw segment starts from,
+// S_j = T^(SEG*j) S (j = 1..G-1), and lane 0 the state of the next refill, T^(G*SEG) S — one
+// matrix per lane, split by state BYTE: e[(j*16 + b)*256 + v] is the image of byte b (bits 8b..8b+7
+// of s0|s1|s2|s3) having value v; the product is the XOR of the 16 selected entries.  No lane
+// waits for another one (the cooperative product of the warp kernel needs a reduction over the
+// G lanes per step, and redux.sync with a partial member mask compiles to a loop).
+struct JumpBytes {
+    uint4 e[1];     // [G][16][256], allocated with the size for G
+};
+constexpr size_t jump_bytes_size(int lanes) { return (size_t)lanes * 16 * 256 * sizeof(uint4); }
+
 // One launch evaluates `n_starts` start positions x P playouts each.  Unit of work: global
 // playout id g = start*P + p; this engine runs the ids with g % shard_count == shard_rank.
 // Units are handed out dynamically from `work_counter` (playout length varies 360..600 moves
@@ -68,7 +80,8 @@ struct KernelArgs {
     const Position* starts;     // [n_starts] device (thread kernel)
     const PaddedPosition* pstarts;  // [n_starts] device (warp kernel)
     const GroupPosition* gstarts;   // [n_starts] device (group kernel)
-    const JumpTable* jump;      // device
+    const JumpTable* jump;      // device (warp kernel)
+    const uint4* jump_bytes;    // device (group kernel), JumpBytes for the launch's lanes per playout
     const StartDesc* descs;     // [n_starts] device
     int32_t n_starts;
     int64_t P;
@@ -98,6 +111,7 @@ void to_group(const Position& p, GroupPosition* out);
 constexpr int kJumpSteps = 16;             // draws each lane generates per ring refill, both kernels
 int jump_steps();
 void build_jump(const RngParams& prm, int steps, JumpTable* out);
+void build_jump_bytes(const RngParams& prm, int lanes, int seg, uint4* out);   // jump_bytes_size(lanes) bytes
 // bounds violations counted by the AGB_CHECK_BOUNDS build of the warp kernel (0 in release)
 unsigned long long debug_violations();
 // coverage counters of the same build (see playout_warp.cu); 0 in release

@@ -141,47 +141,30 @@ AGB_DEV Ev eval_point(const uint32_t* w, uint32_t agent, int idx, int ko_key) {
 }
 
 // ---- rand(): ring refill ------------------------------------------------------------------------
-// The next BATCH = G*SEG draws of the playouts that take part (`part`, a per-group predicate).  The
-// serial part is the G segment-start states: TinyMT32's transition is linear over GF(2), T^SEG is a
-// nibble table (JumpTable), every lane of the group looks up its 32/G nibbles and the group folds
-// them with redux.xor; each state is parked in the ring segment of the lane that will generate from
-// it.  Then every lane generates its SEG draws.  Groups that do not take part run along and store
-// nothing.
+// The next BATCH = G*SEG draws of the playouts that take part (`part`, a per-group predicate).
+// TinyMT32's transition is linear over GF(2): lane j of the group multiplies the generator state
+// (the same in all its lanes) by its own matrix T^(SEG*j) — 16 byte-table lookups (JumpBytes), no
+// other lane involved — and generates the SEG draws of its segment from there; lane 0, whose
+// segment starts at the state itself, computes the state of the next refill instead and hands it
+// to the group.  Groups that do not take part run along and store nothing.
 struct GenState {
     uint32_t g0, g1, g2, g3, gen_end;
 };
 template <class C>
-AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* __restrict__ tab,
-                             int gl, unsigned gmask) {
-    constexpr int NPL = 32 / C::G;                  // nibbles per lane
-    const int widx = (gl * NPL) >> 3;
-    const uint32_t sh0 = (uint32_t)((gl * NPL) & 7) * 4u;
-    const uint4* __restrict__ mytab = tab + gl * NPL * 16;
-    uint4* park = reinterpret_cast<uint4*>(ring + (st.gen_end & (uint32_t)(C::R - 1)));
-    uint32_t a0 = st.g0, a1 = st.g1, a2 = st.g2, a3 = st.g3;
-#pragma unroll 2
-    for (int l = 0; l < C::G; l++) {
-        if (part) park[(C::SEG / 8) * l] = make_uint4(a0, a1, a2, a3);
-        const uint32_t word = widx == 0 ? a0 : (widx == 1 ? a1 : (widx == 2 ? a2 : a3));
-        const uint32_t bits = word >> sh0;
-        uint4 t = __ldg(mytab + (bits & 15u));
+AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* __restrict__ jb,
+                             int gl, int gbase) {
+    const uint4* __restrict__ tab = jb + gl * (16 * 256);
+    uint4 t = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int n = 1; n < NPL; n++) {
-            const uint4 u = __ldg(mytab + n * 16 + ((bits >> (4 * n)) & 15u));
-            t.x ^= u.x; t.y ^= u.y; t.z ^= u.z; t.w ^= u.w;
-        }
-        a0 = __reduce_xor_sync(gmask, t.x);
-        a1 = __reduce_xor_sync(gmask, t.y);
-        a2 = __reduce_xor_sync(gmask, t.z);
-        a3 = __reduce_xor_sync(gmask, t.w);
+    for (int b = 0; b < 16; b++) {
+        const uint32_t word = b < 4 ? st.g0 : (b < 8 ? st.g1 : (b < 12 ? st.g2 : st.g3));
+        const uint4 u = __ldg(tab + b * 256 + ((word >> (8 * (b & 3))) & 255u));
+        t.x ^= u.x; t.y ^= u.y; t.z ^= u.z; t.w ^= u.w;
     }
-    __syncwarp();
     TinyMT mine;
-    {
-        const uint4 s = park[(C::SEG / 8) * gl];
-        mine.s0 = s.x; mine.s1 = s.y; mine.s2 = s.z; mine.s3 = s.w;
-    }
-    __syncwarp();
+    mine.s0 = gl ? t.x : st.g0; mine.s1 = gl ? t.y : st.g1; mine.s2 = gl ? t.z : st.g2; mine.s3 = gl ? t.w : st.g3;
+    const uint32_t n0 = __shfl_sync(kFull, t.x, gbase), n1 = __shfl_sync(kFull, t.y, gbase);
+    const uint32_t n2 = __shfl_sync(kFull, t.z, gbase), n3 = __shfl_sync(kFull, t.w, gbase);
     uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
 #pragma unroll 2
     for (int j = 0; j < C::SEG / 2; j++) {
@@ -192,7 +175,7 @@ AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams p
         if (part) out[j] = lo | (hi << 16);
     }
     __syncwarp();
-    if (part) { st.g0 = a0; st.g1 = a1; st.g2 = a2; st.g3 = a3; st.gen_end += (uint32_t)C::BATCH; }
+    if (part) { st.g0 = n0; st.g1 = n1; st.g2 = n2; st.g3 = n3; st.gen_end += (uint32_t)C::BATCH; }
     return st;
 }
 
@@ -292,12 +275,11 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
     const int gl = lane & (G - 1);
     const int gbase = lane & ~(G - 1);
     const int grp = lane / G;
-    const unsigned gmask = C::GM << gbase;
     uint32_t* const gsm = smem_warp + grp * C::words;
     uint16_t* const ring = reinterpret_cast<uint16_t*>(gsm + C::oRing);
     uint32_t* const w = gsm + C::oBoard;
     uint16_t* const elist = reinterpret_cast<uint16_t*>(gsm + C::oElist);
-    const uint4* __restrict__ jt = a.jump->e;
+    const uint4* __restrict__ jt = a.jump_bytes;
 
     // lane constants: direction of the stone update (lanes 4k..4k+3 = up, left, down, right) and
     // cell of the 3x3 block around the opponent's last move (centre skipped)
@@ -405,7 +387,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
 #define AGB_ENSURE(needpred, k)                                                                     \
         if (__any_sync(kFull, (needpred) && gs.gen_end - pos < (uint32_t)(k))) {                     \
             const bool part_ = live && gs.gen_end - pos <= (uint32_t)(C::R - C::BATCH);              \
-            gs = refill<C>(part_, ring, gs, a.rng, jt, gl, gmask);                                   \
+            gs = refill<C>(part_, ring, gs, a.rng, jt, gl, gbase);                                   \
         }
 
         // ---- Board::getRandomPiece, Board.cpp:341-411 ----
@@ -431,7 +413,9 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
             const bool ok = onb && !e.bad && (G == 8 || gl < 8);
             uint32_t bits = (ok && e.kill ? 1u << c8 : 0u) | (ok && e.survive ? 0x100u << c8 : 0u) |
                             (ok && e.chase ? 0x10000u << c8 : 0u);
-            bits = __reduce_or_sync(gmask, bits);
+            // OR over the group (redux.sync with a partial member mask compiles to a loop)
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) bits |= __shfl_xor_sync(kFull, bits, o);
             if (__any_sync(kFull, bits != 0)) {
                 // iteration k of `for (k = 0; k < 9; k++)` consumes draws 2k, 2k+1; lane k looks at it
                 // (G == 8: the ninth iteration is looked at by every lane of the group)

@@ -70,14 +70,14 @@ extern "C" long long emu_group_playouts(int n, int lanes, const uint32_t* moves,
     to_group(start, &gp);
     StartDesc d = {position_id, cand_idx, (int16_t)colour, (int16_t)first, avrg_win, 0};
     RngParams prm = {AGB_TINYMT_MAT1, AGB_TINYMT_MAT2, AGB_TINYMT_TMAT};
-    JumpTable* jt = new JumpTable;
-    build_jump(prm, jump_steps(), jt);
+    std::vector<uint4> jb(jump_bytes_size(lanes) / sizeof(uint4));
+    build_jump_bytes(prm, lanes, kJumpSteps, jb.data());
     unsigned long long work = 0, stats[kStatCount] = {0, 0, 0, 0};
     long long counters[3] = {0, 0, 0};
     KernelArgs a;
     memset(&a, 0, sizeof(a));
     a.gstarts = &gp;
-    a.jump = jt;
+    a.jump_bytes = jb.data();
     a.descs = &d;
     a.n_starts = 1;
     a.P = P;
@@ -92,7 +92,6 @@ extern "C" long long emu_group_playouts(int n, int lanes, const uint32_t* moves,
     a.max_moves = max_moves > 0 ? max_moves : kDefaultMaxMoves;
     const uint64_t before = emu::collectives_run();
     int st = lanes == 8 ? dispatch<8>(n, a) : (lanes == 16 ? dispatch<16>(n, a) : (lanes == 32 ? dispatch<32>(n, a) : -1));
-    delete jt;
     if (st) return -1;
     out3[0] = counters[0]; out3[1] = counters[1]; out3[2] = counters[2];
     for (int i = 0; i < kStatCount; i++) stat4[i] = (int64_t)stats[i];
