@@ -75,8 +75,8 @@ struct GCfg {
     static constexpr int E = group_elist_cap(N);    // elist entries (kernel_args.h)
     // shared-memory words of one playout: ring | board | elist, a multiple of 4 (the ring is
     // written with 128-bit stores)
-    static constexpr int oRing = 0, oBoard = R / 2, oElist = oBoard + NP;
-    static constexpr int words = ((oElist + E / 2 + 3) / 4) * 4;
+    static constexpr int oRing = 0, oBoard = R / 2, oElist = oBoard + NP, oCbuf = oElist + (E + 1) / 2;
+    static constexpr int words = ((oCbuf + G / 2 + 3) / 4) * 4;    // cbuf: G 16-bit entries, the candidates of a move
     static constexpr int warp_words = NG * words;
     static constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
 };
@@ -279,6 +279,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
     uint16_t* const ring = reinterpret_cast<uint16_t*>(gsm + C::oRing);
     uint32_t* const w = gsm + C::oBoard;
     uint16_t* const elist = reinterpret_cast<uint16_t*>(gsm + C::oElist);
+    uint16_t* const cbuf = reinterpret_cast<uint16_t*>(gsm + C::oCbuf);
     const uint4* __restrict__ jt = a.jump_bytes;
 
     // lane constants: direction of the stone update (lanes 4k..4k+3 = up, left, down, right) and
@@ -290,6 +291,13 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
     const int off_cell = (cc / 3 - 1) * W + (cc % 3 - 1);
     const unsigned qmask = 15u << (lane & ~3);
     const int qbase = lane & ~3;
+
+    // A group that never gets a playout (fewer units than groups) still runs along with safe
+    // indices; what it reads must not send it out of the block's shared memory: all words zero
+    // (an empty point whose root is point 0).
+#pragma unroll 1
+    for (int i = lane; i < C::warp_words; i += 32) smem_warp[i] = 0;
+    __syncwarp();
 
     // state of this lane's playout, the same in all G lanes of the group
     enum { kFetch = 0, kPlay = 1, kEnded = 2, kDone = 3 };
@@ -400,83 +408,122 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
         if (search) n_dead = -1;                                                // put stops maintaining elist
         int r = -1;
         bool found = false;
-        // neighbourhood phase, :354-380: the 8 cells around the opponent's last move, one lane each.
-        // (:356 also wants that stone to be still there; inside a playout it always is, and for the
-        // first move of a playout that was settled when it was set up.)
+        // Both sampling loops of the reference (neighbourhood :354-380, rejection :382-406) consume two
+        // rand() per iteration whatever happens inside, and their predicates are pure functions of a
+        // state that does not change inside the loops.  So ONE evaluation pass serves both: its items
+        // are the empty cells among the 8 around the opponent's last move and, in the lanes that
+        // leaves, the first empty points of the rejection loop's pairs (which start 18 draws further on
+        // when there is a neighbourhood phase).  Pairs are scanned G at a time — looking at a pair is
+        // cheap, evaluating a point is not — until the pass is full or kScan pairs were seen.  The
+        // neighbourhood decides first; if it accepts nothing the rejection candidates are looked at in
+        // draw order; if they were all bad the next pass continues after the pairs this one settled.
+        // (:356 also wants the opponent's last stone to be still there; inside a playout it always is,
+        // and for the first move of a playout that was settled when it was set up.)
         const bool nbact = search && prev >= 0;
-        if (__any_sync(kFull, nbact)) {
-            AGB_ENSURE(nbact, 18)
-            const int cidx0 = nbact ? prev + off_cell : W + 1;
-            const bool onb = nbact && isEmpty(w[cidx0]);                        // empty => on the board
-            const int cidx = onb ? cidx0 : W + 1;
-            const Ev e = eval_point<W, kEvAll>(w, colour, cidx, ko_key);
-            const bool ok = onb && !e.bad && (G == 8 || gl < 8);
-            uint32_t bits = (ok && e.kill ? 1u << c8 : 0u) | (ok && e.survive ? 0x100u << c8 : 0u) |
-                            (ok && e.chase ? 0x10000u << c8 : 0u);
-            // OR over the group (redux.sync with a partial member mask compiles to a loop)
-#pragma unroll
-            for (int o = 1; o < G; o <<= 1) bits |= __shfl_xor_sync(kFull, bits, o);
-            if (__any_sync(kFull, bits != 0)) {
-                // iteration k of `for (k = 0; k < 9; k++)` consumes draws 2k, 2k+1; lane k looks at it
-                // (G == 8: the ninth iteration is looked at by every lane of the group)
-                const unsigned K = bits & 0xffu, S = (bits >> 8) & 0xffu, Cm = bits >> 16;
-                bool hit; int pt;
-                {
-                    const uint32_t ra = mod_small<3>(ring[(pos + 2u * gl) & RM]);
-                    const uint32_t rb = mod_small<3>(ring[(pos + 2u * gl + 1u) & RM]);
-                    const uint32_t c9 = ra * 3u + rb;
-                    const uint32_t cx = c9 - (c9 > 4u);
-                    const unsigned m = K | (gl < 6 ? S : 0u) | (gl < 4 ? Cm : 0u);
-                    hit = gl < 9 && c9 != 4u && ((m >> cx) & 1u);               // the centre is occupied
-                    pt = prev + (int)(ra * W + rb) - (W + 1);
-                }
-                unsigned hm = (__ballot_sync(kFull, hit) >> gbase) & C::GM;
-                int pt8 = -1;
-                if (G == 8) {
-                    const uint32_t ra = mod_small<3>(ring[(pos + 16u) & RM]);
-                    const uint32_t rb = mod_small<3>(ring[(pos + 17u) & RM]);
-                    const uint32_t c9 = ra * 3u + rb;
-                    const uint32_t cx = c9 - (c9 > 4u);
-                    if (c9 != 4u && ((K >> cx) & 1u)) hm |= 0x100u;
-                    pt8 = prev + (int)(ra * W + rb) - (W + 1);
-                }
-                const int k = __ffs(hm) - 1;
-                const int ptk = __shfl_sync(kFull, pt, gbase + (k & (G - 1)));
-                if (nbact && hm) {
-                    pos += 2u * (uint32_t)(k + 1);
-                    r = (G == 8 && k == 8) ? pt8 : ptk;
-                    found = true;
-                }
-            }
-            if (nbact && !found) pos += 18;     // nine iterations, two draws each, none accepted
-        }
-        // rejection loop, :382-406: G pairs per round, lane j looks at pair j.  lim = the pairs that
-        // may still be accepted: the 100th draw is consumed but never accepted (:402-405)
         {
-            int lim = kEndingThreshold - 1;
-            bool rej = search && !found;
+            constexpr int kScan = 32;           // pairs looked at per pass (their index has 5 bits in an item)
+            int lim = kEndingThreshold - 1;     // rejection pairs that may still be accepted: the 100th draw is
+                                                // consumed but never accepted (:402-405)
+            bool rej = search;
+            bool first_pass = true;
+            const unsigned lt = (1u << gl) - 1u;
 #pragma unroll 1
             while (__any_sync(kFull, rej)) {
-                AGB_ENSURE(rej, 2 * G)
-                const uint32_t row = mod_small<C::N>(ring[(pos + 2u * gl) & RM]);
-                const uint32_t cl = mod_small<C::N>(ring[(pos + 2u * gl + 1u) & RM]);
-                const int idx = (int)(row * W + cl) + (W + 1);
-                const bool can = rej && gl < lim && isEmpty(w[idx]);
-                const Ev e = eval_point<W, kEvBad>(w, colour, idx, ko_key);
-                const unsigned good = (__ballot_sync(kFull, can && !e.bad) >> gbase) & C::GM;
-                const int k = __ffs(good) - 1;
-                const int ptk = __shfl_sync(kFull, idx, gbase + (k & (G - 1)));
+                AGB_ENSURE(rej, 18 + 2 * kScan)
+                const uint32_t off18 = (first_pass && nbact) ? 18u : 0u;
+                unsigned nmask = 0;
+                int n_items = 0;
+                if (first_pass) {
+                    const int cidx0 = nbact ? prev + off_cell : W + 1;
+                    const bool nb_empty = nbact && (G == 8 || gl < 8) && isEmpty(w[cidx0]);     // empty => on the board
+                    nmask = (__ballot_sync(kFull, nb_empty) >> gbase) & C::GM;
+                    if (nb_empty) cbuf[__popc(nmask & lt)] = (uint16_t)((uint32_t)cidx0 | 0x8000u);
+                    n_items = __popc(nmask);
+                }
+                // pairs whose fate this pass settles: those scanned, or those before the first empty one
+                // that found no room
+                int covered = -1;
+                int b = 0;
+#pragma unroll 1
+                do {
+                    const int jp = b + gl;
+                    const uint32_t row = mod_small<C::N>(ring[(pos + off18 + 2u * (uint32_t)jp) & RM]);
+                    const uint32_t cl = mod_small<C::N>(ring[(pos + off18 + 2u * (uint32_t)jp + 1u) & RM]);
+                    const int ridx = (int)(row * W + cl) + (W + 1);
+                    const bool can = rej && covered < 0 && jp < lim && isEmpty(w[ridx]);
+                    const unsigned emask = (__ballot_sync(kFull, can) >> gbase) & C::GM;
+                    const int rank = n_items + __popc(emask & lt);
+                    if (can && rank < G) cbuf[rank] = (uint16_t)((uint32_t)ridx | ((uint32_t)jp << 9));
+                    const unsigned over = (__ballot_sync(kFull, can && rank == G) >> gbase) & C::GM;
+                    if (over) covered = b + __ffs(over) - 1;
+                    n_items = min(G, n_items + __popc(emask));
+                    b += G;
+                } while (b < kScan && __any_sync(kFull, rej && covered < 0 && n_items < G && b < lim));
+                if (covered < 0) covered = b;
+                __syncwarp();
+                const bool has = gl < n_items;
+                const uint32_t item = has ? (uint32_t)cbuf[gl] : (uint32_t)(W + 1);
+                const Ev e = eval_point<W, kEvAll>(w, colour, (int)(item & 511u), ko_key);
+                const bool ok = has && !e.bad;
+                const bool is_nb = (item & 0x8000u) != 0;
+                const unsigned goodr = (__ballot_sync(kFull, ok && !is_nb) >> gbase) & C::GM;
+                if (first_pass) {
+                    // by item: neighbourhood items come first, in cell order
+                    const unsigned Kb = (__ballot_sync(kFull, ok && is_nb && e.kill) >> gbase) & C::GM;
+                    const unsigned Sb = (__ballot_sync(kFull, ok && is_nb && e.survive) >> gbase) & C::GM;
+                    const unsigned Cb = (__ballot_sync(kFull, ok && is_nb && e.chase) >> gbase) & C::GM;
+                    if (__any_sync(kFull, (Kb | Sb | Cb) != 0)) {
+                        // iteration k of `for (k = 0; k < 9; k++)` consumes draws 2k, 2k+1; lane k looks at
+                        // it (G == 8: the ninth iteration is looked at by every lane of the group)
+                        bool hit; int pt;
+                        {
+                            const uint32_t ra = mod_small<3>(ring[(pos + 2u * gl) & RM]);
+                            const uint32_t rb = mod_small<3>(ring[(pos + 2u * gl + 1u) & RM]);
+                            const uint32_t c9 = ra * 3u + rb;
+                            const uint32_t cx = c9 - (c9 > 4u);
+                            const unsigned m = Kb | (gl < 6 ? Sb : 0u) | (gl < 4 ? Cb : 0u);
+                            const unsigned ip = (unsigned)__popc(nmask & ((1u << cx) - 1u));        // item of cell cx
+                            hit = gl < 9 && c9 != 4u && ((nmask >> cx) & 1u) && ((m >> ip) & 1u);   // the centre is occupied
+                            pt = prev + (int)(ra * W + rb) - (W + 1);
+                        }
+                        unsigned hm = (__ballot_sync(kFull, hit) >> gbase) & C::GM;
+                        int pt8 = -1;
+                        if (G == 8) {
+                            const uint32_t ra = mod_small<3>(ring[(pos + 16u) & RM]);
+                            const uint32_t rb = mod_small<3>(ring[(pos + 17u) & RM]);
+                            const uint32_t c9 = ra * 3u + rb;
+                            const uint32_t cx = c9 - (c9 > 4u);
+                            const unsigned ip = (unsigned)__popc(nmask & ((1u << cx) - 1u));
+                            if (c9 != 4u && ((nmask >> cx) & 1u) && ((Kb >> ip) & 1u)) hm |= 0x100u;
+                            pt8 = prev + (int)(ra * W + rb) - (W + 1);
+                        }
+                        const int k = __ffs(hm) - 1;
+                        const int ptk = __shfl_sync(kFull, pt, gbase + (k & (G - 1)));
+                        if (nbact && hm) {
+                            pos += 2u * (uint32_t)(k + 1);
+                            r = (G == 8 && k == 8) ? pt8 : ptk;
+                            found = true;
+                            rej = false;
+                        }
+                    }
+                }
+                const int gp = __ffs(goodr) - 1;
+                const uint32_t win = __shfl_sync(kFull, item, gbase + (gp & (G - 1)));
                 if (rej) {
-                    if (good) {
-                        r = ptk; found = true; rej = false;
-                        pos += 2u * (uint32_t)(k + 1);
+                    pos += off18;       // nine iterations, two draws each, none accepted
+                    if (goodr) {
+                        r = (int)(win & 511u);
+                        found = true;
+                        rej = false;
+                        pos += 2u * (((win >> 9) & 31u) + 1u);
                     } else {
-                        const int B = min(G, lim + 1);                          // pairs consumed by this round
-                        pos += 2u * (uint32_t)B;
-                        lim -= B;
+                        const int used = min(covered, lim + 1);                // pairs consumed by this pass
+                        pos += 2u * (uint32_t)used;
+                        lim -= used;
                         if (lim < 0) { ending = 1; cplx = true; rej = false; }
                     }
                 }
+                first_pass = false;
             }
         }
         // complex mode, :413-478: all 32 lanes for one group at a time

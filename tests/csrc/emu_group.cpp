@@ -32,9 +32,12 @@ template <class C>
 void run(const KernelArgs& a) {
     Job<C> j;
     j.a = a;
-    std::vector<uint32_t> smem((size_t)C::warp_words + 64, 0xdeadbeefu);
-    j.smem = (uint32_t*)(((uintptr_t)smem.data() + 63) & ~(uintptr_t)63);
+    // exactly the warp's share of the block's shared memory (a sanitizer build sees any access past it)
+    uint32_t* smem = (uint32_t*)aligned_alloc(64, (((size_t)C::warp_words * 4 + 63) / 64) * 64);
+    for (int i = 0; i < C::warp_words; i++) smem[i] = 0xdeadbeefu;
+    j.smem = smem;
     emu::run_warp(&lane_entry<C>, &j);
+    free(smem);
 }
 
 template <int G>

@@ -5,6 +5,7 @@ namespace emu {
 
 thread_local Warp* g_warp = nullptr;
 static thread_local uint64_t g_total_collectives = 0;
+static uint64_t g_site_count[4096];     // EMU_SITES=1: how often each call site (source line) ran
 
 // save the callee-saved registers on the current stack, switch stacks, restore (System V x86-64)
 asm(R"(
@@ -125,6 +126,7 @@ static void resolve(Warp* w) {
                 abort();
             }
     w->n_collectives++;
+    g_site_count[w->site[0] & 4095]++;
     w->trace[w->n_collectives & 63] = w->site[0];
     if (w->limit && w->n_collectives > w->limit) {
         fprintf(stderr, "simt_emu: more than %llu collectives in one warp (EMU_MAX_COLLECTIVES); last sites:", (unsigned long long)w->limit);
@@ -187,6 +189,11 @@ void run_warp(void (*entry)(int lane, void* user), void* user) {
         resolve(w);
     }
     g_total_collectives += w->n_collectives;
+    if (getenv("EMU_SITES")) {
+        for (int i = 0; i < 4096; i++)
+            if (g_site_count[i]) fprintf(stderr, "site line %d: %llu\n", i, (unsigned long long)g_site_count[i]);
+        memset(g_site_count, 0, sizeof(g_site_count));
+    }
     g_warp = saved;
     for (int l = 0; l < 32; l++) free(w->stack[l]);
     delete w;
