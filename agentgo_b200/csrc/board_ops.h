@@ -74,15 +74,15 @@ struct TinyMT {
         s1 = s2;
         s2 = x ^ (y << 10);
         s3 = y;
-        uint32_t m = (uint32_t)(-(int32_t)(y & 1u));
-        s1 ^= m & mat1;
-        s2 ^= m & mat2;
+        // (selects, not masks: one test and two predicated XORs instead of negate, two ANDs, two XORs)
+        const bool odd = (y & 1u) != 0;
+        s1 = odd ? s1 ^ mat1 : s1;
+        s2 = odd ? s2 ^ mat2 : s2;
     }
     AGB_HD uint32_t temper(uint32_t tmat) const {
         uint32_t t1 = s0 + (s2 >> 8);
         uint32_t t0 = s3 ^ t1;
-        t0 ^= (uint32_t)(-(int32_t)(t1 & 1u)) & tmat;
-        return t0;
+        return (t1 & 1u) ? t0 ^ tmat : t0;
     }
     AGB_HD void init(uint32_t seed, uint32_t mat1, uint32_t mat2, uint32_t tmat) {
         uint32_t st[4] = {seed, mat1, mat2, tmat};

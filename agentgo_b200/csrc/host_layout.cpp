@@ -51,15 +51,15 @@ void to_padded(const Position& p, PaddedPosition* out) {
 void to_group(const Position& p, GroupPosition* out) {
     const int n = p.n, w = n + 2;
     auto pad = [&](int idx) { return (idx / n + 1) * w + (idx % n + 1); };
-    for (int i = 0; i < kMaxNP; i++) out->w[i] = ((uint32_t)kBorder << 30) | (uint32_t)(i < 512 ? i : 0);
+    for (int i = 0; i < kMaxNP; i++) out->w[i] = gw::border((uint32_t)i);
     for (int idx = 0; idx < n * n; idx++) {
         const uint32_t v0 = p.w0[idx], v1 = p.w1[idx];
         const int col = (int)((v0 >> 20) & 3u);
         const int a = (int)(v0 & 1023u), b = (int)((v0 >> 10) & 1023u);
-        if (col == 0) { out->w[pad(idx)] = (uint32_t)pad(idx); continue; }      // the slot is filled in below
+        if (col == 0) { out->w[pad(idx)] = gw::empty((uint32_t)pad(idx), 0); continue; }   // the slot is filled in below
         const bool is_root = a == idx;
-        out->w[pad(idx)] = (uint32_t)pad(a) | ((uint32_t)(b == kNil ? 511 : pad(b)) << 9) |
-                           ((is_root ? (v1 & 0x7ffu) : 0u) << 18) | ((uint32_t)col << 30);
+        out->w[pad(idx)] = gw::stone((uint32_t)pad(a), (uint32_t)(b == kNil ? 511 : pad(b)), is_root ? (v1 & 0x7ffu) : 0u,
+                                     (uint32_t)col);
     }
     // the second stone of every string names the string's last stone
     for (int idx = 0; idx < n * n; idx++) {
@@ -68,7 +68,7 @@ void to_group(const Position& p, GroupPosition* out) {
         const int second = (int)((v0 >> 10) & 1023u);
         if (second == kNil) continue;
         const int tail = (int)(p.w1[idx] >> 16);
-        out->w[pad(second)] = (out->w[pad(second)] & ~(0x7ffu << 18)) | ((uint32_t)pad(tail) << 18);
+        out->w[pad(second)] = (out->w[pad(second)] & ~(0x7ffu << gw::kFShift)) | ((uint32_t)pad(tail) << gw::kFShift);
     }
     int order[kMaxNN], m = 0;
     for (int idx = p.head; idx >= 0 && m < n * n;) {
@@ -82,7 +82,7 @@ void to_group(const Position& p, GroupPosition* out) {
     for (int k = 0; k < m; k++) {
         const int c = pad(order[m - 1 - k]);
         el[k] = (uint16_t)c;
-        out->w[c] = (uint32_t)c | ((uint32_t)k << 9);
+        out->w[c] = gw::empty((uint32_t)c, (uint32_t)k);
     }
     out->n_el = (int16_t)m;
     out->stones = (int16_t)(p.num_black + p.num_white);

@@ -40,12 +40,24 @@ struct PaddedPosition {
 
 // Device layout of a start position for the group kernel (playout_group.cuh): ONE word per point of
 // the padded board,
-//   bits 0-8 A | bits 9-17 next | bits 18-28 F | bits 30-31 colour
+//   bits 0-1 colour | bits 2-10 A | bits 11-19 next | bits 21-31 F
 //        stone:  A = root of its string, next = next stone of the string (511 = end),
 //                F = pseudo-liberties at the root stone / the string's last stone at its SECOND stone
-//        empty:  A = the point itself, next = slot of the point in `elist`
-//        border: A = the point itself, colour 3
+//        empty:  A = the point itself, next = slot of the point in `elist`, F = 1
+//        border: A = the point itself, colour 3, F = 1
+// (A sits at bit 2 so that `w & 0x7fc` is the byte offset of the root's word; F is at the top so
+// that the liberties of a root are one shift away; F = 1 on points without a stone makes "liberties
+// minus multiplicity" zero there, which keeps the byte-packed arithmetic of eval_point borrow free)
 // and the same append-only array of empty points as PaddedPosition.
+namespace gw {
+constexpr int kAShift = 2, kNextShift = 11, kFShift = 21;
+constexpr uint32_t kOne = 1u << kFShift;
+AGB_HD constexpr uint32_t stone(uint32_t root, uint32_t next, uint32_t f, uint32_t col) {
+    return col | (root << kAShift) | (next << kNextShift) | (f << kFShift);
+}
+AGB_HD constexpr uint32_t empty(uint32_t self, uint32_t slot) { return (self << kAShift) | (slot << kNextShift) | kOne; }
+AGB_HD constexpr uint32_t border(uint32_t self) { return 3u | (self << kAShift) | kOne; }
+}  // namespace gw
 constexpr int group_elist_cap(int n) { return n * n + 15; }    // entries in shared memory; compacted when full
 struct GroupPosition {
     uint32_t w[kMaxNP];

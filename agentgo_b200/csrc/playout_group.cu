@@ -32,14 +32,14 @@ cudaError_t launch_g(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchIn
 }  // namespace
 
 cudaError_t launch_playout_group(int n, int lanes, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    // 8 lanes per playout: 72 playouts per SM (3 040 B each at 19x19) in 18 warps of 112 registers;
+    // 8 lanes per playout: 76 playouts per SM (3 056 B each at 19x19) in one block of 19 warps, 104 registers;
     // 16 lanes: 64 playouts in 32 warps of 64 registers; 32 lanes (the mapping of playout_warp.cu
     // run through this code, for comparison): 32 playouts in 32 warps.
     if (lanes == 8) {
         switch (n) {
-            case 9: return launch_g<9, 8, 9, 2>(a, sm_count, s, info);
-            case 13: return launch_g<13, 8, 9, 2>(a, sm_count, s, info);
-            case 19: return launch_g<19, 8, 9, 2>(a, sm_count, s, info);
+            case 9: return launch_g<9, 8, 19, 1>(a, sm_count, s, info);
+            case 13: return launch_g<13, 8, 19, 1>(a, sm_count, s, info);
+            case 19: return launch_g<19, 8, 19, 1>(a, sm_count, s, info);
         }
     } else if (lanes == 16) {
         switch (n) {

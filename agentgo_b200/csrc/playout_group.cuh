@@ -19,16 +19,18 @@
 //  * RARE BULK WORK BORROWS THE WHOLE WARP.  Clone, scoring, complex mode
 //    (Board::getRandomPieceComplex) and the compaction of the empty-point array serve one group at
 //    a time with all 32 lanes (the board of any group of the warp is in reach of every lane).
-//  * One 32-bit word per point (the warp kernel had two), padded (N+2)^2 board:
-//        bits 0-8   A     stone: root of its string; empty / border point: its own index
-//        bits 9-17  next  stone: next stone of the string in SetNode::pieces order (511 = end);
+//  * One 32-bit word per point (the warp kernel had two), padded (N+2)^2 board (kernel_args.h, gw::):
+//        bits 0-1   colour (0 empty, 1 black, 2 white, 3 border)
+//        bits 2-10  A     stone: root of its string; empty / border point: its own index
+//        bits 11-19 next  stone: next stone of the string in SetNode::pieces order (511 = end);
 //                         empty point: its slot in the empty-point array `elist`
-//        bits 18-28 F     root stone: pseudo-liberties (SetNode::hp); SECOND stone of a string: the
+//        bits 21-31 F     root stone: pseudo-liberties (SetNode::hp); SECOND stone of a string: the
 //                         string's last stone (the tail is needed only when strings are joined, the
-//                         root on every lookup, so the root keeps the field that is one AND away)
-//        bits 30-31 colour (0 empty, 1 black, 2 white, 3 border)
+//                         liberties on every lookup, so the root keeps the field that is one shift
+//                         away); 1 on empty and border points
 //    With A = own index on empty and border points the root of "whatever is next to a point" is
-//    w & 511 with no case split, and equal roots mean the same string.
+//    one AND away with no case split (w & 0x7fc is even its byte offset), and equal roots mean
+//    the same string.
 //  * The empty-point list is the append-only array of the warp kernel (kernel_args.h), the rand()
 //    ring too, but smaller (R = 2*G*SEG entries), refilled whenever a phase is about to read past
 //    its end: state per playout 3.1 KB at 19x19, 72 playouts per SM.
@@ -54,17 +56,24 @@ namespace grp {
 
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kNilG = 511u;
-constexpr uint32_t kHpOne = 1u << 18;
-constexpr uint32_t kHpMask = 0x7ffu << 18;
-constexpr uint32_t kNextMask = 511u << 9;
+constexpr uint32_t kHpOne = gw::kOne;
+constexpr uint32_t kHpMask = 0x7ffu << gw::kFShift;
+constexpr uint32_t kNextMask = 511u << gw::kNextShift;
+constexpr uint32_t kAMask = 511u << gw::kAShift;
 constexpr uint32_t kResFlag = 0x8000u;     // elist entry: point is reserved in the current complex-mode call
 
-AGB_DEV uint32_t fA(uint32_t w) { return w & 511u; }
-AGB_DEV uint32_t fNext(uint32_t w) { return (w >> 9) & 511u; }
-AGB_DEV uint32_t fHp(uint32_t w) { return (w >> 18) & 0x7ffu; }
-AGB_DEV uint32_t fCol(uint32_t w) { return w >> 30; }
-AGB_DEV bool isEmpty(uint32_t w) { return w < 0x40000000u; }
-AGB_DEV bool isStone(uint32_t w) { return (int32_t)(w + 0x40000000u) < 0; }
+AGB_DEV uint32_t fA(uint32_t w) { return (w >> gw::kAShift) & 511u; }
+AGB_DEV uint32_t offA(uint32_t w) { return w & kAMask; }                 // byte offset of the root's word
+AGB_DEV uint32_t fNext(uint32_t w) { return (w >> gw::kNextShift) & 511u; }
+AGB_DEV uint32_t fHp(uint32_t w) { return w >> gw::kFShift; }
+AGB_DEV uint32_t fCol(uint32_t w) { return w & 3u; }
+AGB_DEV bool isEmpty(uint32_t w) { return (w & 3u) == 0; }
+AGB_DEV uint32_t setA(uint32_t w, uint32_t a) { return (w & ~kAMask) | (a << gw::kAShift); }
+AGB_DEV uint32_t setNext(uint32_t w, uint32_t n) { return (w & ~kNextMask) | (n << gw::kNextShift); }
+AGB_DEV uint32_t setF(uint32_t w, uint32_t f) { return (w & ~kHpMask) | (f << gw::kFShift); }
+AGB_DEV uint32_t at(const uint32_t* w, uint32_t byte_off) {              // the word at a byte offset
+    return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(w) + byte_off);
+}
 
 template <int N_, int G_, int SEG_>
 struct GCfg {
@@ -93,49 +102,74 @@ AGB_DEV uint32_t mod_small(uint32_t v) {
 // point idx for `agent`, computed by one lane from the 4 + 4 words around it.
 //   reserve = true eye | suicide | ko            (complex mode: no checkDying, :425-427)
 //   bad     = reserve | dying                    (the filter of both sampling phases)
-enum { kEvAll = 0, kEvBad = 1, kEvRes = 2 };
+// The four directions are the four BYTES of a register: colours, liberties (clamped to 255, which
+// no test below can tell from the true value) and multiplicities are packed once, classes come out
+// of the carry-free "byte != 0" trick as 0x80 flags, sums out of dp4a.  Thirty booleans kept in
+// predicates made the compiler spill them into a register bit by bit (220 instructions per call).
+enum { kEvAll = 0, kEvRes = 2 };
 struct Ev {
     bool kill, survive, chase, bad;     // kEvRes: bad = reserve
 };
+constexpr uint32_t k80 = 0x80808080u, k7f = 0x7f7f7f7fu, k01 = 0x01010101u;
+// 0x80 in every byte of x that is not zero; the bytes of x are below 0x80
+AGB_DEV uint32_t nz_small(uint32_t x) { return (x + k7f) & k80; }
+// the same for any bytes
+AGB_DEV uint32_t nz_bytes(uint32_t x) { return (((x & k7f) + k7f) | x) & k80; }
 template <int W, int MODE>
 AGB_DEV Ev eval_point(const uint32_t* w, uint32_t agent, int idx, int ko_key) {
-    const uint32_t enemy = 3u - agent;
+    const uint32_t agent4 = agent * k01;
     const uint32_t v0 = w[idx - W], v1 = w[idx - 1], v2 = w[idx + W], v3 = w[idx + 1];
-    const uint32_t r0 = fA(v0), r1 = fA(v1), r2 = fA(v2), r3 = fA(v3);
-    const int h0 = (int)fHp(w[r0]), h1 = (int)fHp(w[r1]), h2 = (int)fHp(w[r2]), h3 = (int)fHp(w[r3]);
-    const uint32_t c0 = fCol(v0), c1 = fCol(v1), c2 = fCol(v2), c3 = fCol(v3);
-    // a string seen from several directions counts once, less its multiplicity (minus_hp, :506-515)
-    const bool e01 = r0 == r1, e02 = r0 == r2, e03 = r0 == r3, e12 = r1 == r2, e13 = r1 == r3, e23 = r2 == r3;
-    const int l0 = h0 - 1 - e01 - e02 - e03, l1 = h1 - 1 - e01 - e12 - e13;
-    const int l2 = h2 - 1 - e02 - e12 - e23, l3 = h3 - 1 - e03 - e13 - e23;
-    const bool en0 = c0 == enemy, en1 = c1 == enemy, en2 = c2 == enemy, en3 = c3 == enemy;
-    const bool fr0 = c0 == agent, fr1 = c1 == agent, fr2 = c2 == agent, fr3 = c3 == agent;
-    const int n_empty = (c0 == 0) + (c1 == 0) + (c2 == 0) + (c3 == 0);
-    const bool ecap = (en0 && l0 == 0) || (en1 && l1 == 0) || (en2 && l2 == 0) || (en3 && l3 == 0);
-    const bool fsafe = (fr0 && l0 > 0) || (fr1 && l1 > 0) || (fr2 && l2 > 0) || (fr3 && l3 > 0);
+    // colours of up, left, down, right in bytes 0..3
+    const uint32_t cb = __byte_perm(__byte_perm(v0, v1, 0x0040), __byte_perm(v2, v3, 0x0040), 0x5410) & 0x03030303u;
+    const uint32_t xf = cb ^ agent4;                        // zero byte: own stone
+    const uint32_t nF = nz_small(xf), nE = nz_small(xf ^ 0x03030303u), nZ = nz_small(cb);    // 0x80: NOT own / enemy / empty
+    const uint32_t F80 = nF ^ k80, E80 = nE ^ k80;
+    const int n_empty = 4 - __popc(nZ);
+    // liberties of the strings around (1 on a point without a stone, see gw::), less the number of
+    // directions that see the same string (minus_hp, :506-515)
+    const uint32_t o0 = offA(v0), o1 = offA(v1), o2 = offA(v2), o3 = offA(v3);
+    const uint32_t h0 = min(fHp(at(w, o0)), 255u), h1 = min(fHp(at(w, o1)), 255u);
+    const uint32_t h2 = min(fHp(at(w, o2)), 255u), h3 = min(fHp(at(w, o3)), 255u);
+    const uint32_t H = h0 | (h1 << 8) | (h2 << 16) | (h3 << 24);
+    const bool e01 = o0 == o1, e02 = o0 == o2, e03 = o0 == o3, e12 = o1 == o2, e13 = o1 == o3, e23 = o2 == o3;
+    const uint32_t M = k01 + (e01 ? 0x00000101u : 0u) + (e02 ? 0x00010001u : 0u) + (e03 ? 0x01000001u : 0u) +
+                       (e12 ? 0x00010100u : 0u) + (e13 ? 0x01000100u : 0u) + (e23 ? 0x01010000u : 0u);
+    const uint32_t L = H - M;                               // left = hp - multiplicity, per byte
+    const uint32_t nL0 = nz_bytes(L);                       // 0x80: left != 0
+    const bool ecap = (E80 & ~nL0) != 0;                    // an enemy string is captured
+    const bool fsafe = (F80 & nL0) != 0;                    // an own string keeps a liberty
     const bool suicide = n_empty == 0 && !ecap && !fsafe;                       // :480-524
-    // Board::checkTrueEye, :735-751: a point is on the edge iff an orthogonal neighbour is border
-    const bool own4 = (fr0 || c0 == 3) && (fr1 || c1 == 3) && (fr2 || c2 == 3) && (fr3 || c3 == 3);
-    const bool edge = c0 == 3 || c1 == 3 || c2 == 3 || c3 == 3;
-    const int cnt = (fCol(w[idx - W - 1]) == enemy) + (fCol(w[idx - W + 1]) == enemy) +
-                    (fCol(w[idx + W - 1]) == enemy) + (fCol(w[idx + W + 1]) == enemy);
-    const bool eye = own4 && cnt < (edge ? 1 : 2);
+    // Board::checkTrueEye, :735-751: nothing but own stones and border around, and fewer than two
+    // enemy stones on the diagonals (none on the edge: an orthogonal neighbour is border there)
+    const bool own4 = (E80 | (nZ ^ k80)) == 0;              // no enemy stone, no empty point
+    const bool edge = (nF & nE & nZ) != 0;                  // neither own nor enemy nor empty: border
+    bool eye = false;
+    if (own4) {
+        const uint32_t d0 = w[idx - W - 1], d1 = w[idx - W + 1], d2 = w[idx + W - 1], d3 = w[idx + W + 1];
+        const uint32_t db = __byte_perm(__byte_perm(d0, d1, 0x0040), __byte_perm(d2, d3, 0x0040), 0x5410) & 0x03030303u;
+        const int cnt = 4 - __popc(nz_small(db ^ agent4 ^ 0x03030303u));
+        eye = cnt < (edge ? 1 : 2);
+    }
     const bool ko = ko_key == (int)((agent << 16) | (uint32_t)idx);             // :753-755
     Ev e;
     e.kill = e.survive = e.chase = false;
     e.bad = eye || suicide || ko;
     if (MODE == kEvRes) return e;
-    const bool f1 = !e01, f2 = !(e02 || e12), f3 = !(e03 || e13 || e23);        // first sight of the string
-    const int fsum = (fr0 ? l0 : 0) + (fr1 && f1 ? l1 : 0) + (fr2 && f2 ? l2 : 0) + (fr3 && f3 ? l3 : 0);
-    const int tot = n_empty + fsum;
+    // own strings count once, where they are first seen
+    const uint32_t first = k01 & ~((e01 ? 0x00000100u : 0u) | ((e02 || e12) ? 0x00010000u : 0u) |
+                                   ((e03 || e13 || e23) ? 0x01000000u : 0u));
+    const int tot = n_empty + (int)__dp4a(first & (F80 >> 7), L, 0u);
     e.bad = e.bad || (!ecap && tot == 1);                                       // checkDying, :628-679
     if (MODE == kEvAll) {
-        const bool eatari = (en0 && l0 == 1) || (en1 && l1 == 1) || (en2 && l2 == 1) || (en3 && l3 == 1);
-        const bool fcap = (fr0 && l0 == 0) || (fr1 && l1 == 0) || (fr2 && l2 == 0) || (fr3 && l3 == 0);
-        const int fmin = min(min(fr0 ? h0 : 9999, fr1 ? h1 : 9999), min(fr2 ? h2 : 9999, fr3 ? h3 : 9999));
+        const bool eatari = (E80 & ~nz_bytes(L ^ k01)) != 0;                    // an enemy string is left with one
+        const bool fcap = (F80 & ~nL0) != 0;                                    // an own string has none left
         e.kill = ecap;                                                          // :526-563
-        e.survive = fcap && (ecap || tot > fmin);                               // :565-626
         e.chase = eatari && tot > 1;                                            // :681-733
+        if (fcap) {                                                             // :565-626
+            const uint32_t hf = H | ((nF >> 7) * 255u);     // 255 where the neighbour is not an own stone
+            const uint32_t fmin = min(min(hf & 255u, (hf >> 8) & 255u), min((hf >> 16) & 255u, hf >> 24));
+            e.survive = ecap || tot > (int)fmin;
+        }
     }
     return e;
 }
@@ -166,13 +200,15 @@ AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams p
     const uint32_t n0 = __shfl_sync(kFull, t.x, gbase), n1 = __shfl_sync(kFull, t.y, gbase);
     const uint32_t n2 = __shfl_sync(kFull, t.z, gbase), n3 = __shfl_sync(kFull, t.w, gbase);
     uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
+    if (part) {         // (no collective inside: the lanes of a group that does not take part just wait)
 #pragma unroll 2
-    for (int j = 0; j < C::SEG / 2; j++) {
-        mine.next_state(prm.mat1, prm.mat2);
-        const uint32_t lo = mine.temper(prm.tmat) >> 17;
-        mine.next_state(prm.mat1, prm.mat2);
-        const uint32_t hi = mine.temper(prm.tmat) >> 17;
-        if (part) out[j] = lo | (hi << 16);
+        for (int j = 0; j < C::SEG / 2; j++) {
+            mine.next_state(prm.mat1, prm.mat2);
+            const uint32_t lo = mine.temper(prm.tmat) >> 17;
+            mine.next_state(prm.mat1, prm.mat2);
+            const uint32_t hi = mine.temper(prm.tmat) >> 17;
+            out[j] = lo | (hi << 16);
+        }
     }
     __syncwarp();
     if (part) { st.g0 = n0; st.g1 = n1; st.g2 = n2; st.g3 = n3; st.gen_end += (uint32_t)C::BATCH; }
@@ -197,7 +233,7 @@ AGB_NOINLINE int compact(uint32_t* w, uint16_t* elist, int n_el, int lane) {
         if (alive) {
             const int o = out + __popc(m & ((1u << lane) - 1u));
             elist[o] = (uint16_t)c;
-            w[c] = c | ((uint32_t)o << 9);
+            w[c] = gw::empty(c, (uint32_t)o);
         }
         out += __popc(m);
     }
@@ -414,14 +450,16 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
         // are the empty cells among the 8 around the opponent's last move and, in the lanes that
         // leaves, the first empty points of the rejection loop's pairs (which start 18 draws further on
         // when there is a neighbourhood phase).  Pairs are scanned G at a time — looking at a pair is
-        // cheap, evaluating a point is not — until the pass is full or kScan pairs were seen.  The
+        // cheap, evaluating a point is not — until the pass holds kWant of them or kScan pairs were seen.  The
         // neighbourhood decides first; if it accepts nothing the rejection candidates are looked at in
         // draw order; if they were all bad the next pass continues after the pairs this one settled.
         // (:356 also wants the opponent's last stone to be still there; inside a playout it always is,
         // and for the first move of a playout that was settled when it was set up.)
         const bool nbact = search && prev >= 0;
         {
-            constexpr int kScan = 32;           // pairs looked at per pass (their index has 5 bits in an item)
+            constexpr int kScan = 32;           // pairs looked at per pass at most (their index has 5 bits in an item)
+            constexpr int kWant = 3;            // ... until the pass holds this many rejection candidates: one
+                                                // more scan round costs a fifth of one more pass
             int lim = kEndingThreshold - 1;     // rejection pairs that may still be accepted: the 100th draw is
                                                 // consumed but never accepted (:402-405)
             bool rej = search;
@@ -432,13 +470,13 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 AGB_ENSURE(rej, 18 + 2 * kScan)
                 const uint32_t off18 = (first_pass && nbact) ? 18u : 0u;
                 unsigned nmask = 0;
-                int n_items = 0;
+                int n_items = 0, n_nb = 0;
                 if (first_pass) {
                     const int cidx0 = nbact ? prev + off_cell : W + 1;
                     const bool nb_empty = nbact && (G == 8 || gl < 8) && isEmpty(w[cidx0]);     // empty => on the board
                     nmask = (__ballot_sync(kFull, nb_empty) >> gbase) & C::GM;
                     if (nb_empty) cbuf[__popc(nmask & lt)] = (uint16_t)((uint32_t)cidx0 | 0x8000u);
-                    n_items = __popc(nmask);
+                    n_items = n_nb = __popc(nmask);
                 }
                 // pairs whose fate this pass settles: those scanned, or those before the first empty one
                 // that found no room
@@ -458,7 +496,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     if (over) covered = b + __ffs(over) - 1;
                     n_items = min(G, n_items + __popc(emask));
                     b += G;
-                } while (b < kScan && __any_sync(kFull, rej && covered < 0 && n_items < G && b < lim));
+                } while (b < kScan && __any_sync(kFull, rej && covered < 0 && n_items < G && n_items - n_nb < kWant && b < lim));
                 if (covered < 0) covered = b;
                 __syncwarp();
                 const bool has = gl < n_items;
@@ -623,35 +661,37 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 const bool own = act && frnd && firstl;
                 if (own) {
                     const uint32_t tw = w[tail];
-                    w[tail] = (tw & ~kNextMask) | (target << 9);
+                    w[tail] = setNext(tw, target);
                 }
                 // strings F_1..F_(k-1) are relabelled to Fk (:284-289), each by its own lane
                 bool walk = own && root != fk;
                 uint32_t cur = root;
 #pragma unroll 1
                 while (__any_sync(kFull, walk)) {
-                    if (walk) {
-                        const uint32_t cw = w[cur];
-                        w[cur] = (cw & ~511u) | fk;
-                        walk = cur != tail;
-                        cur = fNext(cw);
-                    }
+#pragma unroll
+                    for (int u = 0; u < 2; u++)
+                        if (walk) {
+                            const uint32_t cw = w[cur];
+                            w[cur] = setA(cw, fk);
+                            walk = cur != tail;
+                            cur = fNext(cw);
+                        }
                 }
                 __syncwarp();
                 if (own && root == fk) {
                     const uint32_t rw2 = w[fk];
-                    w[fk] = (rw2 & ~kHpMask) | ((uint32_t)hp_total << 18);
+                    w[fk] = setF(rw2, (uint32_t)hp_total);
                     // the new stone is the last one; the second stone of Fk says so
                     const uint32_t sec = nx != kNilG ? nx : target;
                     if (sec != (uint32_t)idx) {
                         const uint32_t x = w[sec];
-                        w[sec] = (x & ~kHpMask) | ((uint32_t)idx << 18);
+                        w[sec] = setF(x, (uint32_t)idx);
                     }
                 }
             }
             // SetNode::init (SetNode.cpp:31-44) for a stone on its own, else the last stone of Fk
             if (doput && gl == 0)
-                w[idx] = fk | (kNilG << 9) | ((frq ? (uint32_t)idx : (uint32_t)hp_self) << 18) | (colour << 30);
+                w[idx] = gw::stone(fk, kNilG, frq ? (uint32_t)idx : (uint32_t)hp_self, colour);
             __syncwarp();
             // Board::killSetNode, :293-339: one captured stone per group and step; lanes 0..3 of the
             // group give the liberty back to the strings around it (increments commute: atomics)
@@ -660,18 +700,21 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 bool single = false;
 #pragma unroll 1
                 for (;;) {
-                    const int dcap = caps ? __ffs(caps) - 1 : 0;
-                    const uint32_t victim = __shfl_sync(kFull, root, qbase + dcap);
-                    if (kcur == kNilG && caps) {
-                        caps &= caps - 1u;
-                        kcur = victim;
-                        single = fNext(w[victim]) == kNilG;
+                    const bool want = kcur == kNilG && caps != 0;
+                    if (__any_sync(kFull, want)) {
+                        const uint32_t victim = __shfl_sync(kFull, root, qbase + (caps ? __ffs(caps) - 1 : 0));
+                        if (want) {
+                            caps &= caps - 1u;
+                            kcur = victim;
+                            single = fNext(w[victim]) == kNilG;
+                        }
                     }
                     if (!__any_sync(kFull, kcur != kNilG)) break;
                     // the array is full: drop its stale entries (all 32 lanes per group)
                     unsigned full = __ballot_sync(kFull, kcur != kNilG && n_el == C::E);
 #pragma unroll 1
                     while (full) {
+                        __syncwarp();       // the stones this loop has taken off so far
                         const int X = (__ffs(full) - 1) / G;
                         const int src = X * G;
                         full &= ~(C::GM << src);
@@ -681,22 +724,24 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                         if (grp == X) { n_el = xn; if (n_dead > 0) n_dead = 0; }
                     }
                     // (the group's first lane rewrites the stone's word below: the link is read by it
-                    // alone, before that, and handed to the others)
+                    // alone, before that, and handed to the others.  Nothing else written here is
+                    // read before the loop ends: the neighbours looked at are tested for the mover's
+                    // colour, which neither a captured stone nor the empty point it becomes has.)
                     const uint32_t nxk = __shfl_sync(kFull, fNext(w[kcur != kNilG ? kcur : 0]), gbase);
                     if (kcur != kNilG) {
-                        const uint32_t vn = w[(int)kcur + off_nb];                   // one liberty back, :323-326
+                        const uint32_t vn = w[(int)kcur + off_nb];              // one liberty back, :323-326
                         if (act && fCol(vn) == colour) atomicAdd(&w[fA(vn)], kHpOne);
                         stones--;
                         if (gl == 0) {
                             elist[n_el] = (uint16_t)kcur;                       // push at the list head, :311-321
-                            w[kcur] = kcur | ((uint32_t)n_el << 9);             // empty, slot = n_el
+                            w[kcur] = gw::empty(kcur, (uint32_t)n_el);          // empty, slot = n_el
                         }
                         n_el++;
                         if (single) ko_key = (int)(((3u - colour) << 16) | kcur);   // :328-333
                         kcur = nxk;
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
         }
 

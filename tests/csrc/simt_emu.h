@@ -93,6 +93,21 @@ inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline int __clz(unsigned x) { return x ? __builtin_clz(x) : 32; }
 inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((uint64_t)a * b) >> 32); }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
+    const uint64_t src = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        const unsigned sel = (s >> (4 * i)) & 0xfu;
+        unsigned b = (unsigned)(src >> (8 * (sel & 7u))) & 0xffu;
+        if (sel & 8u) b = (b & 0x80u) ? 0xffu : 0u;     // sign replication
+        r |= b << (8 * i);
+    }
+    return r;
+}
+inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+    return c;
+}
 template <typename T>
 inline T __ldg(const T* p) { return *p; }
 // the lanes of the emulated warp run one at a time, so plain read-modify-write is atomic
