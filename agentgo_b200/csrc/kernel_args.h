@@ -72,13 +72,14 @@ struct JumpTable {
     uint4 e[32 * 16];
 };
 
-// Jump tables of the group kernel: lane j of a playout's G lanes computes by itself, from the
-// generator state S at draw number gen_end, the state its own SEG-draw segment starts from,
-// S_j = T^(SEG*j) S (j = 1..G-1), and lane 0 the state of the next refill, T^(G*SEG) S — one
-// matrix per lane, split by state BYTE: e[(j*16 + b)*256 + v] is the image of byte b (bits 8b..8b+7
-// of s0|s1|s2|s3) having value v; the product is the XOR of the 16 selected entries.  No lane
-// waits for another one (the cooperative product of the warp kernel needs a reduction over the
-// G lanes per step, and redux.sync with a partial member mask compiles to a loop).
+// Jump tables of the group kernel.  Lane j of a playout's G lanes generates draws [j*SEG, (j+1)*SEG)
+// of every batch of G*SEG draws from a generator state of its own.  Matrix 0 is T^(G*SEG), the step
+// from one batch to the next (the same for every lane); matrix j = 1..G-1 is T^(SEG*j), the step from
+// the seed state to lane j's first segment.  Each is split by state BYTE: e[(j*16 + b)*256 + v] is
+// the image of byte b (bits 8b..8b+7 of s0|s1|s2|s3) having value v; a product is the XOR of the
+// 16 selected entries.  No lane waits for another one (the cooperative product of the warp kernel
+// needs a reduction over the lanes per step, and redux.sync with a partial member mask compiles to
+// a loop).
 struct JumpBytes {
     uint4 e[1];     // [G][16][256], allocated with the size for G
 };

@@ -176,31 +176,35 @@ AGB_DEV Ev eval_point(const uint32_t* w, uint32_t agent, int idx, int ko_key) {
 
 // ---- rand(): ring refill ------------------------------------------------------------------------
 // The next BATCH = G*SEG draws of the playouts that take part (`part`, a per-group predicate).
-// TinyMT32's transition is linear over GF(2): lane j of the group multiplies the generator state
-// (the same in all its lanes) by its own matrix T^(SEG*j) — 16 byte-table lookups (JumpBytes), no
-// other lane involved — and generates the SEG draws of its segment from there; lane 0, whose
-// segment starts at the state itself, computes the state of the next refill instead and hands it
-// to the group.  Groups that do not take part run along and store nothing.
+// Lane j of a playout's G lanes generates draws [j*SEG, (j+1)*SEG) of every batch, and keeps for
+// that a generator state of its OWN: the state its segment of the next batch starts from.  TinyMT32's
+// transition is linear over GF(2), so that state moves from one batch to the next by the same
+// matrix for every lane, T^BATCH: 16 byte-table lookups (JumpBytes, matrix 0), no other lane
+// involved.  The lookups depend only on the state the segment starts from, so they are issued first
+// and their latency (the table lives in L2) is covered by generating the segment.  When a playout
+// is set up lane j jumps from the seed state by T^(SEG*j) (matrix j).  Groups that do not take
+// part run along and store nothing.
 struct GenState {
-    uint32_t g0, g1, g2, g3, gen_end;
+    uint32_t g0, g1, g2, g3;    // this lane's state at draw gen_end + SEG * (lane in group)
+    uint32_t gen_end;           // draws [pos, gen_end) of the playout are in the ring
 };
-template <class C>
-AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* __restrict__ jb,
-                             int gl, int gbase) {
-    const uint4* __restrict__ tab = jb + gl * (16 * 256);
+AGB_DEV uint4 jump_lookup(const uint4* __restrict__ tab, uint32_t g0, uint32_t g1, uint32_t g2, uint32_t g3) {
     uint4 t = make_uint4(0, 0, 0, 0);
 #pragma unroll
     for (int b = 0; b < 16; b++) {
-        const uint32_t word = b < 4 ? st.g0 : (b < 8 ? st.g1 : (b < 12 ? st.g2 : st.g3));
+        const uint32_t word = b < 4 ? g0 : (b < 8 ? g1 : (b < 12 ? g2 : g3));
         const uint4 u = __ldg(tab + b * 256 + ((word >> (8 * (b & 3))) & 255u));
         t.x ^= u.x; t.y ^= u.y; t.z ^= u.z; t.w ^= u.w;
     }
-    TinyMT mine;
-    mine.s0 = gl ? t.x : st.g0; mine.s1 = gl ? t.y : st.g1; mine.s2 = gl ? t.z : st.g2; mine.s3 = gl ? t.w : st.g3;
-    const uint32_t n0 = __shfl_sync(kFull, t.x, gbase), n1 = __shfl_sync(kFull, t.y, gbase);
-    const uint32_t n2 = __shfl_sync(kFull, t.z, gbase), n3 = __shfl_sync(kFull, t.w, gbase);
-    uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
+    return t;
+}
+template <class C>
+AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* __restrict__ jb, int gl) {
+    const uint4 t = jump_lookup(jb, st.g0, st.g1, st.g2, st.g3);       // matrix 0: T^BATCH
     if (part) {         // (no collective inside: the lanes of a group that does not take part just wait)
+        TinyMT mine;
+        mine.s0 = st.g0; mine.s1 = st.g1; mine.s2 = st.g2; mine.s3 = st.g3;
+        uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
 #pragma unroll 2
         for (int j = 0; j < C::SEG / 2; j++) {
             mine.next_state(prm.mat1, prm.mat2);
@@ -209,9 +213,10 @@ AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams p
             const uint32_t hi = mine.temper(prm.tmat) >> 17;
             out[j] = lo | (hi << 16);
         }
+        st.g0 = t.x; st.g1 = t.y; st.g2 = t.z; st.g3 = t.w;
+        st.gen_end += (uint32_t)C::BATCH;
     }
     __syncwarp();
-    if (part) { st.g0 = n0; st.g1 = n1; st.g2 = n2; st.g3 = n3; st.gen_end += (uint32_t)C::BATCH; }
     return st;
 }
 
@@ -408,6 +413,9 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 // tinymt32_init (RFC 8682)
                 TinyMT t;
                 t.init(playout_seed(a.seed_base, d.position_id, d.cand_idx, (uint64_t)p), a.rng.mat1, a.rng.mat2, a.rng.tmat);
+                // this lane's segment of the first batch starts SEG * gl draws further on (matrix gl)
+                const uint4 js = jump_lookup(jt + gl * (16 * 256), t.s0, t.s1, t.s2, t.s3);
+                if (gl != 0) { t.s0 = js.x; t.s1 = js.y; t.s2 = js.z; t.s3 = js.w; }
                 if (grp == X) {
                     phase = kPlay;
                     colour = first = (uint32_t)d.first;
@@ -431,7 +439,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
 #define AGB_ENSURE(needpred, k)                                                                     \
         if (__any_sync(kFull, (needpred) && gs.gen_end - pos < (uint32_t)(k))) {                     \
             const bool part_ = live && gs.gen_end - pos <= (uint32_t)(C::R - C::BATCH);              \
-            gs = refill<C>(part_, ring, gs, a.rng, jt, gl, gbase);                                   \
+            gs = refill<C>(part_, ring, gs, a.rng, jt, gl);                                   \
         }
 
         // ---- Board::getRandomPiece, Board.cpp:341-411 ----
