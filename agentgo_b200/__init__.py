@@ -31,7 +31,7 @@ SYMBOLS = [
     "agb_get_board", "agb_check", "agb_count_score", "agb_export_state", "agb_playouts",
     "agb_playouts_amaf", "agb_playouts_launch", "agb_playouts_finish", "agb_counters_dev", "agb_stream",
     "agb_set_allreduce", "agb_playouts_batch", "agb_genmove", "agb_measure_peaks",
-    "agb_debug_violations", "agb_attach_nccl", "agb_detach_nccl", "agb_static_units", "agb_last_marks",
+    "agb_debug_violations", "agb_attach_nccl", "agb_detach_nccl", "agb_set_allgather", "agb_static_units", "agb_last_marks",
     "agb_genmove_step", "agb_set_genmove_step", "agb_calc_result", "agb_random_piece", "agb_debug_event",
 ]
 
@@ -63,6 +63,7 @@ class PositionC(C.Structure):
 
 
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)
 
 _lib = None
 
@@ -112,6 +113,7 @@ def lib():
     l.agb_stream.argtypes = [vp]
     l.agb_stream.restype = vp
     l.agb_set_allreduce.argtypes = [vp, ALLREDUCE_FN, vp]
+    l.agb_set_allgather.argtypes = [vp, ALLGATHER_FN, vp]
     l.agb_playouts_batch.argtypes = [vp, C.POINTER(PositionC), C.c_int, C.c_int64, C.c_uint64,
                                      C.c_uint32, i64p, i64p, i64p, i16p, C.POINTER(Stats)]
     l.agb_genmove.argtypes = [vp, C.c_int, C.c_int64, C.c_int64, C.c_uint64,
@@ -376,3 +378,13 @@ class Engine:
             return
         self._cb = ALLREDUCE_FN(lambda ctx, ptr, count, stream: int(fn(ptr, count, stream) or 0))
         self._chk(self._l.agb_set_allreduce(self._h, self._cb, None))
+
+    def set_allgather(self, fn):
+        """fn(send_ptr:int, recv_ptr:int, count_per_shard:int, stream:int) -> 0; gathers the int64 tables of
+        all shards in shard order (the collective of playouts_batch on sharded engines)."""
+        if fn is None:
+            self._cbg = None
+            self._chk(self._l.agb_set_allgather(self._h, C.cast(None, ALLGATHER_FN), None))
+            return
+        self._cbg = ALLGATHER_FN(lambda ctx, send, recv, count, stream: int(fn(send, recv, count, stream) or 0))
+        self._chk(self._l.agb_set_allgather(self._h, self._cbg, None))

@@ -177,6 +177,12 @@ int agb_set_allreduce(agb_engine* h, agb_allreduce_fn fn, void* ctx) {
     return AGB_OK;
 }
 
+int agb_set_allgather(agb_engine* h, agb_allgather_fn fn, void* ctx) {
+    if (!h) return AGB_ERR_INVALID;
+    h->e->set_allgather((agb::AllgatherFn)fn, ctx);
+    return AGB_OK;
+}
+
 int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P, uint64_t seed_base,
                        uint32_t first_position_id, int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
                        int16_t* per_playout_diff, agb_stats* stats) {

@@ -92,7 +92,7 @@ Engine::~Engine() {
     cudaSetDevice(cfg.device);
     if (stream_) cudaStreamSynchronize(stream_);
     cudaFree(d_starts_); cudaFree(d_descs_); cudaFree(d_counters_); cudaFree(d_diffs_);
-    cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_amaf_);
+    cudaFree(d_gather_); cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_amaf_);
     if (h_pinned_) cudaFreeHost(h_pinned_);
     if (h_stage_) cudaFreeHost(h_stage_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -112,13 +112,14 @@ int Engine::ensure(void** ptr, size_t* cap, size_t bytes) {
 }
 
 int Engine::launch(const std::vector<Position>& starts, const std::vector<StartDesc>& descs, int64_t P,
-                   uint64_t seed_base, bool want_diffs, bool shard_units, bool want_amaf) {
+                   uint64_t seed_base, bool want_diffs, bool shard_units, bool want_amaf, int counter_stride) {
     if (cfg.device < 0) return fail(AGB_ERR_CUDA, "engine was created without a CUDA device (device = -1); no CPU fallback");
     if (in_flight_) return fail(AGB_ERR_STATE, "a launch is already in flight");
     if (starts.empty() || starts.size() != descs.size() || P <= 0)
         return fail(AGB_ERR_INVALID, "nothing to launch");
     AGB_CUDA(cudaSetDevice(cfg.device));
     const int S = (int)starts.size();
+    const int stride = counter_stride > S ? counter_stride : S;
     int st;
     const bool thread_kernel = cfg.kernel == AGB_KERNEL_THREAD;
     if (want_amaf && thread_kernel)
@@ -139,7 +140,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     const size_t start_bytes = (thread_kernel ? sizeof(Position) : (group_lanes ? sizeof(GroupPosition) : sizeof(PaddedPosition))) * (size_t)S;
     if ((st = ensure(&d_starts_, &cap_starts_, start_bytes))) return st;
     if ((st = ensure(&d_descs_, &cap_descs_, sizeof(StartDesc) * (size_t)S))) return st;
-    if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)S))) return st;
+    if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)stride))) return st;
     if (want_diffs && (st = ensure(&d_diffs_, &cap_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P))) return st;
 
     // inputs are staged in PINNED host memory and copied asynchronously on the engine's stream
@@ -162,7 +163,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     memcpy((char*)h_stage_ + start_bytes, descs.data(), desc_bytes);
     AGB_CUDA(cudaMemcpyAsync(d_starts_, h_stage_, start_bytes, cudaMemcpyHostToDevice, stream_));
     AGB_CUDA(cudaMemcpyAsync(d_descs_, (char*)h_stage_ + start_bytes, desc_bytes, cudaMemcpyHostToDevice, stream_));
-    AGB_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(long long) * 3 * (size_t)S, stream_));
+    AGB_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(long long) * 3 * (size_t)stride, stream_));
     AGB_CUDA(cudaMemsetAsync(d_small_, 0, kSmallWords * sizeof(unsigned long long), stream_));
 
     KernelArgs a;
@@ -194,6 +195,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     a.work_counter = (unsigned long long*)d_small_;
     a.stats = (unsigned long long*)d_small_ + 1;
     a.counters = (long long*)d_counters_;
+    a.counter_stride = stride;
     a.diffs = want_diffs ? (int16_t*)d_diffs_ : nullptr;
     a.amaf = want_amaf ? (long long*)d_amaf_ : nullptr;
     a.rng.mat1 = cfg.mat1; a.rng.mat2 = cfg.mat2; a.rng.tmat = cfg.tmat;
@@ -209,7 +211,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     }
     in_flight_ = true;
-    n_starts_ = S; P_ = P; want_diffs_ = want_diffs; shard_units_ = shard_units; want_amaf_ = want_amaf;
+    n_starts_ = S; stride_ = stride; P_ = P; want_diffs_ = want_diffs; shard_units_ = shard_units; want_amaf_ = want_amaf;
     return AGB_OK;
 }
 
@@ -220,7 +222,8 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
     AGB_CUDA(cudaSetDevice(cfg.device));
     const int S = n_starts_;
     // snapshot the shard-local stats before any collective touches the counters
-    const size_t need = sizeof(long long) * 3 * (size_t)S + kSmallWords * sizeof(unsigned long long);
+    const int T = stride_;      // the counter table is [3][T], T >= S
+    const size_t need = sizeof(long long) * 3 * (size_t)T + kSmallWords * sizeof(unsigned long long);
     if (cap_pinned_ < need) {
         if (h_pinned_) cudaFreeHost(h_pinned_);
         h_pinned_ = nullptr; cap_pinned_ = 0;
@@ -228,7 +231,7 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
         cap_pinned_ = need;
     }
     if (allreduce_) {
-        int r = allreduce_(allreduce_ctx_, d_counters_, 3 * S, (void*)stream_);
+        int r = allreduce_(allreduce_ctx_, d_counters_, 3 * T, (void*)stream_);
         if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
         if (want_amaf_) {
             r = allreduce_(allreduce_ctx_, d_amaf_, AGB_AMAF_WORDS(board.n()) * amaf_classes(), (void*)stream_);
@@ -238,8 +241,8 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
     // device time of the evaluation = kernel (+ collective), stream ordered
     AGB_CUDA(cudaEventRecord(ev1_, stream_));
     long long* hc = (long long*)h_pinned_;
-    unsigned long long* hs = (unsigned long long*)(hc + 3 * (size_t)S);
-    AGB_CUDA(cudaMemcpyAsync(hc, d_counters_, sizeof(long long) * 3 * (size_t)S, cudaMemcpyDeviceToHost, stream_));
+    unsigned long long* hs = (unsigned long long*)(hc + 3 * (size_t)T);
+    AGB_CUDA(cudaMemcpyAsync(hc, d_counters_, sizeof(long long) * 3 * (size_t)T, cudaMemcpyDeviceToHost, stream_));
     AGB_CUDA(cudaMemcpyAsync(hs, d_small_, kSmallWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
     if (diffs && want_diffs_ && !(shard_units_ && cfg.shard_count > 1))
         AGB_CUDA(cudaMemcpyAsync(diffs, d_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P_, cudaMemcpyDeviceToHost, stream_));
@@ -257,8 +260,8 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
     }
     for (int s = 0; s < S; s++) {
         if (wins) wins[s] = hc[s];
-        if (sum_pos) sum_pos[s] = hc[S + s];
-        if (sum_neg) sum_neg[s] = hc[2 * S + s];
+        if (sum_pos) sum_pos[s] = hc[T + s];
+        if (sum_neg) sum_neg[s] = hc[2 * T + s];
     }
     float ms = 0.f;
     AGB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
@@ -340,23 +343,69 @@ int Engine::playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t s
         if (sum_neg) sum_neg[b] = 0;
     }
     if (stats) memset(stats, 0, sizeof(*stats));
-    if (starts.empty()) return AGB_OK;
+    if (starts.empty() && !(cfg.shard_count > 1 && allgather_)) return AGB_OK;
     const int S = (int)starts.size();
-    int st = launch(starts, descs, P, seed_base, diffs != nullptr, false);
-    if (st) return st;
+    // Several shards with a gather hook: every shard pads its table to the size of the largest one,
+    // ONE allgather follows the kernel on the engine's stream and every shard returns the whole
+    // [B] table ("shards by position, then one allgather of results").
+    const int R = cfg.shard_count;
+    const bool gather = R > 1 && allgather_ != nullptr;
+    int stride = S;
+    std::vector<int> n_of(R, 0);
+    if (gather) {
+        for (int b = 0; b < B; b++) n_of[(first_position_id + (uint32_t)b) % (uint32_t)R]++;
+        stride = *std::max_element(n_of.begin(), n_of.end());
+    }
+    int st = 0;
+    if (S > 0) {
+        st = launch(starts, descs, P, seed_base, diffs != nullptr, false, false, stride);
+        if (st) return st;
+    } else if (gather) {
+        // nothing to play here, but the collective needs this shard's (empty) table
+        AGB_CUDA(cudaSetDevice(cfg.device));
+        if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)stride))) return st;
+        AGB_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(long long) * 3 * (size_t)stride, stream_));
+    }
+    std::vector<long long> table;
+    if (gather) {
+        const size_t words = (size_t)R * 3 * (size_t)stride;
+        if ((st = ensure(&d_gather_, &cap_gather_, sizeof(long long) * words))) return st;
+        if (allgather_(allgather_ctx_, d_counters_, d_gather_, 3 * stride, (void*)stream_))
+            return fail(AGB_ERR_CUDA, "allgather callback failed");
+        table.resize(words);
+        AGB_CUDA(cudaMemcpyAsync(table.data(), d_gather_, sizeof(long long) * words, cudaMemcpyDeviceToHost, stream_));
+    }
     std::vector<int64_t> w(S), sp(S), sn(S);
     std::vector<int16_t> dl;
     if (diffs) dl.resize((size_t)S * (size_t)P);
-    AllreduceFn saved = allreduce_;
-    allreduce_ = nullptr;       // results of a batch are gathered by the caller, per position
-    st = finish(w.data(), sp.data(), sn.data(), diffs ? dl.data() : nullptr, stats);
-    allreduce_ = saved;
-    if (st) return st;
+    if (S > 0) {
+        AllreduceFn saved = allreduce_;
+        allreduce_ = nullptr;       // results of a batch are gathered per position, not summed
+        st = finish(w.data(), sp.data(), sn.data(), diffs ? dl.data() : nullptr, stats);
+        allreduce_ = saved;
+        if (st) return st;
+    } else if (gather) {
+        AGB_CUDA(cudaStreamSynchronize(stream_));
+    }
+    if (gather) {
+        // position b was slot k of shard r, k counting that shard's positions in batch order
+        std::vector<int> next(R, 0);
+        for (int b = 0; b < B; b++) {
+            const int r = (int)((first_position_id + (uint32_t)b) % (uint32_t)R);
+            const long long* t = table.data() + (size_t)r * 3 * (size_t)stride;
+            const int k = next[r]++;
+            if (wins) wins[b] = t[k];
+            if (sum_pos) sum_pos[b] = t[stride + k];
+            if (sum_neg) sum_neg[b] = t[2 * stride + k];
+        }
+    }
     for (int s = 0; s < S; s++) {
         const int b = owner[s];
-        if (wins) wins[b] = w[s];
-        if (sum_pos) sum_pos[b] = sp[s];
-        if (sum_neg) sum_neg[b] = sn[s];
+        if (!gather) {
+            if (wins) wins[b] = w[s];
+            if (sum_pos) sum_pos[b] = sp[s];
+            if (sum_neg) sum_neg[b] = sn[s];
+        }
         if (diffs) memcpy(diffs + (size_t)b * (size_t)P, dl.data() + (size_t)s * (size_t)P, sizeof(int16_t) * (size_t)P);
     }
     return AGB_OK;

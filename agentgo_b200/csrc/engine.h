@@ -18,6 +18,7 @@
 namespace agb {
 
 typedef int (*AllreduceFn)(void* ctx, void* dev_int64, int count, void* cuda_stream);
+typedef int (*AllgatherFn)(void* ctx, const void* send_dev_int64, void* recv_dev_int64, int count_per_shard, void* cuda_stream);
 
 class Engine {
 public:
@@ -30,7 +31,7 @@ public:
 
     // general launch: starts x P playouts, ids sharded by g % shard_count (by_unit) or all local
     int launch(const std::vector<Position>& starts, const std::vector<StartDesc>& descs, int64_t P,
-               uint64_t seed_base, bool want_diffs, bool shard_units, bool want_amaf = false);
+               uint64_t seed_base, bool want_diffs, bool shard_units, bool want_amaf = false, int counter_stride = 0);
     // waits, copies counters (and diffs) out.  Buffers are [n_starts] / [n_starts*P].
     // amaf: [amaf_classes() * AGB_AMAF_WORDS(n)] or nullptr; only valid after a launch with want_amaf
     int finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats,
@@ -57,6 +58,7 @@ public:
     void* counters_dev() const { return d_counters_; }
     cudaStream_t stream() const { return stream_; }
     void set_allreduce(AllreduceFn fn, void* ctx) { allreduce_ = fn; allreduce_ctx_ = ctx; }
+    void set_allgather(AllgatherFn fn, void* ctx) { allgather_ = fn; allgather_ctx_ = ctx; }
     int fail(int status, const std::string& msg) { err = msg; return status; }
 
 private:
@@ -90,6 +92,10 @@ private:
     LaunchInfo info_ = {0, 0, 0, ""};
     AllreduceFn allreduce_ = nullptr;
     void* allreduce_ctx_ = nullptr;
+    AllgatherFn allgather_ = nullptr;    // batch path: gathers every shard's [3][stride] table
+    void* allgather_ctx_ = nullptr;
+    void* d_gather_ = nullptr; size_t cap_gather_ = 0;
+    int stride_ = 0;                     // counter stride of the launch in flight
 };
 
 }  // namespace agb

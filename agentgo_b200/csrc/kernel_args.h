@@ -102,7 +102,8 @@ struct KernelArgs {
     int32_t shard_rank, shard_count;
     int64_t local_units;        // number of ids this shard owns
     unsigned long long* work_counter;   // device, zeroed before launch
-    long long* counters;        // device [3][n_starts]: wins | sum_pos | sum_neg
+    long long* counters;        // device [3][counter_stride]: wins | sum_pos | sum_neg
+    int32_t counter_stride;     // >= n_starts (the batch path pads every shard's table to the same size)
     int16_t* diffs;             // device [n_starts*P] or nullptr
     long long* amaf;            // device [2 which][2 sign][41 step][N*N] or nullptr (AMAF marks, warp kernel)
     unsigned long long* stats;  // device [4]: moves, rng draws, faults, playouts

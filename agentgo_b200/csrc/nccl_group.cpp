@@ -1,6 +1,7 @@
 // nccl_group.cpp — single-process multi-GPU: N engines (one per GPU, shard i of N) joined by one
 // NCCL communicator, so partial counters are combined with ONE ncclAllReduce (sum, int64) per
-// evaluation over NVLink, issued on each engine's own stream right after its kernel.
+// evaluation over NVLink, issued on each engine's own stream right after its kernel; the batch path
+// (positions sharded, agb_playouts_batch) gathers its per-position table with ONE ncclAllGather.
 //
 // libnccl is opened at run time (dlopen), so the library has no link-time dependency on it and
 // single-GPU use never touches it.  Collectives from several devices of one process must be
@@ -20,6 +21,7 @@ namespace {
 typedef void* ncclComm_t;
 typedef int (*InitAllFn)(ncclComm_t*, int, const int*);
 typedef int (*AllReduceFn)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+typedef int (*AllGatherFn)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t);
 typedef int (*DestroyFn)(ncclComm_t);
 typedef const char* (*ErrStrFn)(int);
 typedef int (*GroupFn)();
@@ -29,6 +31,7 @@ struct Nccl {
     void* lib = nullptr;
     InitAllFn init_all = nullptr;
     AllReduceFn all_reduce = nullptr;
+    AllGatherFn all_gather = nullptr;
     DestroyFn destroy = nullptr;
     ErrStrFn err_str = nullptr;
     std::string error;
@@ -42,9 +45,10 @@ struct Nccl {
         if (!lib) { error = std::string("cannot open libnccl: ") + dlerror(); return false; }
         init_all = (InitAllFn)dlsym(lib, "ncclCommInitAll");
         all_reduce = (AllReduceFn)dlsym(lib, "ncclAllReduce");
+        all_gather = (AllGatherFn)dlsym(lib, "ncclAllGather");
         destroy = (DestroyFn)dlsym(lib, "ncclCommDestroy");
         err_str = (ErrStrFn)dlsym(lib, "ncclGetErrorString");
-        if (!init_all || !all_reduce || !destroy) { error = "libnccl lacks the expected symbols"; return false; }
+        if (!init_all || !all_reduce || !all_gather || !destroy) { error = "libnccl lacks the expected symbols"; return false; }
         return true;
     }
 };
@@ -60,6 +64,14 @@ int hook(void* ctx, void* dev_int64, int count, void* stream) {
     const int r = g_nccl.all_reduce(dev_int64, dev_int64, (size_t)count, kNcclInt64, kNcclSum, m->comm,
                                     (cudaStream_t)stream);
     if (r != 0) fprintf(stderr, "ncclAllReduce: %s\n", g_nccl.err_str ? g_nccl.err_str(r) : "error");
+    return r;
+}
+
+// the batch path: every shard's [count] table into [shards][count], one ncclAllGather
+int gather_hook(void* ctx, const void* send, void* recv, int count, void* stream) {
+    Member* m = (Member*)ctx;
+    const int r = g_nccl.all_gather(send, recv, (size_t)count, kNcclInt64, m->comm, (cudaStream_t)stream);
+    if (r != 0) fprintf(stderr, "ncclAllGather: %s\n", g_nccl.err_str ? g_nccl.err_str(r) : "error");
     return r;
 }
 
@@ -92,6 +104,7 @@ extern "C" int agb_attach_nccl(agb_engine** engines, int n, agb_nccl_group** out
     for (int i = 0; i < n; i++) {
         g->members[i].comm = comms[i];
         engines[i]->e->set_allreduce(hook, &g->members[i]);
+        engines[i]->e->set_allgather(gather_hook, &g->members[i]);
     }
     *out = g;
     return AGB_OK;
@@ -101,6 +114,7 @@ extern "C" void agb_detach_nccl(agb_nccl_group* g) {
     if (!g) return;
     for (size_t i = 0; i < g->engines.size(); i++) {
         g->engines[i]->e->set_allreduce(nullptr, nullptr);
+        g->engines[i]->e->set_allgather(nullptr, nullptr);
         g_nccl.destroy(g->members[i].comm);
     }
     delete g;

@@ -381,9 +381,9 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                         unsigned long long* c = (unsigned long long*)a.counters;
                         if (wr >= 0) {                                           // sign test of AgentGo.cpp:328
                             atomicAdd(&c[xs], 1ull);
-                            atomicAdd(&c[a.n_starts + xs], (unsigned long long)wr);
+                            atomicAdd(&c[a.counter_stride + xs], (unsigned long long)wr);
                         } else {
-                            atomicAdd(&c[2 * a.n_starts + xs], (unsigned long long)(long long)wr);
+                            atomicAdd(&c[2 * a.counter_stride + xs], (unsigned long long)(long long)wr);
                         }
                     }
                 }

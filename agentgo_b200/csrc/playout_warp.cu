@@ -902,9 +902,9 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
                 unsigned long long* c = (unsigned long long*)a.counters;
                 if (w >= 0) {                                        // sign test of AgentGo.cpp:328
                     atomicAdd(&c[s], 1ull);
-                    atomicAdd(&c[a.n_starts + s], (unsigned long long)w);
+                    atomicAdd(&c[a.counter_stride + s], (unsigned long long)w);
                 } else {
-                    atomicAdd(&c[2 * a.n_starts + s], (unsigned long long)(long long)w);
+                    atomicAdd(&c[2 * a.counter_stride + s], (unsigned long long)(long long)w);
                 }
             }
         }

@@ -50,6 +50,50 @@ def attach_allreduce(engine, group=None):
     return hook
 
 
+def batch_layout(B, first_position_id, world):
+    """Where the counters of batch position b live in the gathered table (the rule of
+    Engine::playouts_batch): position b belongs to rank (first_position_id + b) % world and is that
+    rank's k-th position in batch order.  -> (stride = largest local count, [(rank, k)] * B)"""
+    nxt = [0] * world
+    where = []
+    for b in range(B):
+        r = (first_position_id + b) % world
+        where.append((r, nxt[r]))
+        nxt[r] += 1
+    return (max(nxt) if B else 0), where
+
+
+def attach_allgather(engine, group=None):
+    """Install the NCCL allgather hook of the batch path (agb_set_allgather): positions are sharded
+    by id, every shard's [3 x stride] int64 table is gathered in rank order with ONE collective on
+    the engine's own stream."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+
+    def hook(send, recv, count, stream):
+        ext = torch.cuda.ExternalStream(int(stream))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        with torch.cuda.stream(ext):
+            src = torch.as_tensor(_DevInt64(send, count), device=dev)
+            dst = torch.as_tensor(_DevInt64(recv, count * world), device=dev)
+            dist.all_gather_into_tensor(dst, src, group=group)
+        return 0
+
+    engine.set_allgather(hook)
+    return hook
+
+
+def gather_host_tables(table, group=None):
+    """The same gather for int64 numpy tables on the host (gloo; the world_size-2 CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.from_numpy(np.ascontiguousarray(table, dtype=np.int64).copy())
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, t, group=group)
+    return [o.numpy() for o in out]
+
+
 def allreduce_host_counts(arrays, group=None):
     """Sum int64 numpy arrays over the process group (works with gloo on CPU; used by the
     world_size-2 tests of the sharding rule)."""

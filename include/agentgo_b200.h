@@ -214,10 +214,18 @@ void* agb_stream(agb_engine* h);
  * and return 0.  Without it a sharded engine returns its own shard's partial counts.    */
 typedef int (*agb_allreduce_fn)(void* ctx, void* dev_int64, int count, void* cuda_stream);
 int agb_set_allreduce(agb_engine* h, agb_allreduce_fn fn, void* ctx);
+/* The collective of the batch path (agb_playouts_batch on sharded engines): positions are sharded,
+ * every shard fills a table of count_per_shard int64 and fn must gather the tables of all shards,
+ * in shard order, into recv_dev_int64 (one NCCL allgather, ncclInt64, on that stream) and return 0.
+ * With it every shard's agb_playouts_batch returns the counters of ALL positions; without it a
+ * shard returns its own positions and zeros elsewhere (last sentence).           */
+typedef int (*agb_allgather_fn)(void* ctx, const void* send_dev_int64, void* recv_dev_int64,
+                                int count_per_shard, void* cuda_stream);
+int agb_set_allgather(agb_engine* h, agb_allgather_fn fn, void* ctx);
 
 /* Single-process multi-GPU: engines[i] must be shard i of n on its own device.  Builds one NCCL
  * communicator (ncclCommInitAll; libnccl is dlopen'ed at this point) and installs the allreduce
- * hook on every engine.  Afterwards issue the SAME agb_playouts* / agb_genmove call on every engine
+ * and allgather hooks on every engine.  Afterwards issue the SAME agb_playouts* / agb_genmove call on every engine
  * concurrently, one host thread per engine: each returns the counters summed over all GPUs.     */
 typedef struct agb_nccl_group agb_nccl_group;
 int agb_attach_nccl(agb_engine** engines, int n, agb_nccl_group** out);
@@ -244,7 +252,9 @@ int agb_playouts_amaf(agb_engine* h, int colour, const int16_t* cand_rc, int C, 
 /* batch of B independent positions (config 3): root-mode, P playouts each,
  * position b uses position_id = first_position_id + b and is evaluated by the
  * shard with (first_position_id + b) % shard_count == shard_rank.
- * outputs are [B]; per_playout_diff is [B*P] or NULL.                        */
+ * outputs are [B]; per_playout_diff is [B*P] or NULL.  With an allgather hook
+ * (agb_set_allgather / agb_attach_nccl) every shard returns the counters of all B
+ * positions; per_playout_diff stays local to the shard that played them.      */
 int agb_playouts_batch(agb_engine* h, const agb_position* pos, int B, int64_t P,
                        uint64_t seed_base, uint32_t first_position_id,
                        int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,

@@ -72,6 +72,50 @@ def test_world_size_2_gloo(port_lib):
     assert res == [(0, True, True), (1, True, True)]
 
 
+def _batch_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from agentgo_b200 import dist as agdist
+    from oracle import pyoracle as po
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, P, B, first = 9, 60, 5, 3
+    games = [po.OracleBoard(n, "port").random_game(1, 10 + 3 * b, 77 + b) for b in range(B)]
+    full = np.zeros((B, 3), dtype=np.int64)
+    for b in range(B):
+        r = po.OracleBoard(n, "port").replay(games[b]).playouts(1 + len(games[b]) % 2, None, P, position_id=first + b,
+                                                                 want_diffs=False, threads=1)
+        full[b] = [r[0][0], r[1][0], r[2][0]]
+    # this rank's table: [3][stride], its positions in batch order, zero padded (Engine::playouts_batch)
+    stride, where = agdist.batch_layout(B, first, world)
+    table = np.zeros((3, stride), dtype=np.int64)
+    for b, (r, k) in enumerate(where):
+        if r == rank:
+            table[:, k] = full[b]
+    tables = agdist.gather_host_tables(table)
+    got = np.array([tables[r][:, k] for r, k in where])
+    q.put((rank, bool((got == full).all()), int(stride)))
+    dist.destroy_process_group()
+
+
+def test_batch_gather_world_size_2_gloo(port_lib):
+    """Config 3 on N ranks: positions sharded by id, one allgather of the padded tables, every rank
+    reassembles the whole [B x 3] table (last sentence)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_batch_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [(0, True, 3), (1, True, 3)]
+
+
 def test_shard_rule():
     from agentgo_b200 import dist as agdist
     for total in (0, 1, 7, 1000):

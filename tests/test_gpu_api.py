@@ -271,3 +271,34 @@ def test_ragged_batch_and_wide_candidate_sets(built_lib):
         w, sp, sn, d, st = e.playouts(ag.WHITE, cands, P, avrg_win=-2, seed_base=9, want_diffs=True)
         ow, osp, osn, od = ob.playouts(2, cands, P, avrg_win=-2, seed_base=9, threads=0)
         assert (d == od).all() and (w == ow).all() and (sp == osp).all() and (sn == osn).all()
+
+
+def test_batch_gather_on_two_gpus(built_lib):
+    """Config 3 on two GPUs of one box (agb_attach_nccl: positions sharded by id, one ncclAllGather of the
+    per-position table): every engine returns the table a single engine computes."""
+    import ctypes as C
+    import threading
+    l = ag.lib()
+    if l.agb_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    g = golden("midgame_19.npz")
+    pos = [(mv, int(g["to_move"][i])) for i, mv in enumerate(split_moves(g))][:7]
+    P = 256
+    ref = ag.Engine(19).playouts_batch(pos, P, seed_base=5, first_position_id=3)
+    engines = [ag.Engine(19, device=i, shard_rank=i, shard_count=2) for i in range(2)]
+    arr = (C.c_void_p * 2)(*[e._h for e in engines])
+    grp = C.c_void_p()
+    assert l.agb_attach_nccl(arr, 2, C.byref(grp)) == 0
+    out = [None, None]
+
+    def run(i):
+        out[i] = engines[i].playouts_batch(pos, P, seed_base=5, first_position_id=3)
+    ts = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    l.agb_detach_nccl(grp)
+    for i in range(2):
+        assert (out[i][0] == ref[0]).all() and (out[i][1] == ref[1]).all() and (out[i][2] == ref[2]).all()
+        assert out[i][4]["playouts"] == P * len([b for b in range(7) if (3 + b) % 2 == i])
