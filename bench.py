@@ -419,8 +419,8 @@ def run_b200(args):
             extras["genmove_1M"] = {"positions": len(gd), "n_gpus": world, "budget": "1000000 playouts split over the candidates "
                                     "+ 65536 root playouts (avrg_win)", "device_ms_median": pct(gd, 0.5), "device_ms_p95": pct(gd, 0.95),
                                     "wall_ms_median": pct(gw, 0.5), "wall_ms_p95": pct(gw, 0.95),
-                                    "limits": "two kernels (root, candidates) of ~1.07M/N playouts per GPU, each followed by its "
-                                              "allreduce, stream-ordered with no host round trip in between"}
+                                    "limits": "two kernels (root 65536, candidates 1M) of 1/N of the playouts per GPU, each followed by its "
+                                              "allreduce; the last wave of resident playouts of each kernel"}
 
     if rank != 0:
         if tdist is not None:
