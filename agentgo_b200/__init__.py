@@ -47,7 +47,14 @@ class Config(C.Structure):
                 ("shard_rank", C.c_int), ("shard_count", C.c_int),
                 ("mat1", C.c_uint32), ("mat2", C.c_uint32), ("tmat", C.c_uint32),
                 ("max_moves", C.c_int), ("genmove_amaf", C.c_int),
-                ("genmove_static", C.c_int), ("genmove_book", C.c_int)]
+                ("genmove_static", C.c_int), ("genmove_book", C.c_int),
+                ("index_a", C.c_double), ("index_b", C.c_double), ("index_c", C.c_double),
+                ("index_amaf_a1", C.c_double), ("index_amaf_a2", C.c_double),
+                ("index_amaf_b1", C.c_double), ("index_amaf_b2", C.c_double), ("index_cnsv", C.c_double)]
+
+# the eight tunables of the reference's command line, in argv order (AgentGo.cpp:709-719)
+TUNABLES = ("index_a", "index_b", "index_c", "index_amaf_a1", "index_amaf_a2", "index_amaf_b1", "index_amaf_b2",
+            "index_cnsv")
 
 
 class Stats(C.Structure):
@@ -189,13 +196,16 @@ class Engine:
     """
 
     def __init__(self, board_size=13, device=0, kernel=KERNEL_AUTO, shard_rank=0, shard_count=1,
-                 max_moves=0, genmove_amaf=0, genmove_static=0, genmove_book=0):
+                 max_moves=0, genmove_amaf=0, genmove_static=0, genmove_book=0, tunables=None):
         self._l = lib()
         cfg = Config()
         self._l.agb_default_config(C.byref(cfg))
         cfg.board_size, cfg.device, cfg.kernel = board_size, device, kernel
         cfg.shard_rank, cfg.shard_count, cfg.max_moves = shard_rank, shard_count, max_moves
         cfg.genmove_amaf, cfg.genmove_static, cfg.genmove_book = genmove_amaf, genmove_static, genmove_book
+        if tunables is not None:            # eight doubles in the order of the reference's argv, or a dict
+            for k, v in (tunables.items() if isinstance(tunables, dict) else zip(TUNABLES, tunables)):
+                setattr(cfg, k, float(v))
         h = C.c_void_p()
         st = self._l.agb_create(C.byref(cfg), C.byref(h))
         if st:

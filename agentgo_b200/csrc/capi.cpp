@@ -39,6 +39,10 @@ void agb_default_config(agb_config* cfg) {
     cfg->mat2 = AGB_TINYMT_MAT2;
     cfg->tmat = AGB_TINYMT_TMAT;
     cfg->max_moves = 0;
+    /* AgentGo.cpp:18-25 */
+    cfg->index_a = 1000; cfg->index_b = 1; cfg->index_c = 1;
+    cfg->index_amaf_a1 = 40; cfg->index_amaf_a2 = 39. / 180; cfg->index_amaf_b1 = 0.3; cfg->index_amaf_b2 = 0.3 / 180;
+    cfg->index_cnsv = 0.01;
 }
 
 const char* agb_version(void) { return "agentgo_b200 0.1 (sm_100a)"; }

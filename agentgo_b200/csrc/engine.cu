@@ -23,6 +23,18 @@ int Engine::cuda_fail(cudaError_t e, const char* what) {
         if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
     } while (0)
 
+// a caller that zeroed the struct instead of calling agb_default_config gets the reference's values
+static void defaults_for_zero_tunables(agb_config* c) {
+    if (c->index_a == 0 && c->index_b == 0 && c->index_c == 0 && c->index_amaf_a1 == 0 && c->index_amaf_a2 == 0 &&
+        c->index_amaf_b1 == 0 && c->index_amaf_b2 == 0 && c->index_cnsv == 0) {
+        agb_config d;
+        agb_default_config(&d);
+        c->index_a = d.index_a; c->index_b = d.index_b; c->index_c = d.index_c;
+        c->index_amaf_a1 = d.index_amaf_a1; c->index_amaf_a2 = d.index_amaf_a2;
+        c->index_amaf_b1 = d.index_amaf_b1; c->index_amaf_b2 = d.index_amaf_b2; c->index_cnsv = d.index_cnsv;
+    }
+}
+
 int Engine::create(const agb_config& cfg, Engine** out, std::string* err) {
     *out = nullptr;
     if (!HostBoard::size_supported(cfg.board_size)) {
@@ -37,6 +49,7 @@ int Engine::create(const agb_config& cfg, Engine** out, std::string* err) {
         // position-only engine: replay / predicates / export work, every compute call fails
         Engine* h = new Engine();
         h->cfg = cfg;
+        defaults_for_zero_tunables(&h->cfg);
         h->board.reset(cfg.board_size);
         *out = h;
         return AGB_OK;
@@ -58,6 +71,7 @@ int Engine::create(const agb_config& cfg, Engine** out, std::string* err) {
         h->cfg.mat1 = AGB_TINYMT_MAT1; h->cfg.mat2 = AGB_TINYMT_MAT2; h->cfg.tmat = AGB_TINYMT_TMAT;
     }
     if (h->cfg.max_moves <= 0) h->cfg.max_moves = kDefaultMaxMoves;
+    defaults_for_zero_tunables(&h->cfg);
     h->board.reset(cfg.board_size);
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(cfg.device)) != cudaSuccess ||
@@ -455,7 +469,8 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
         if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1, use_amaf ? amaf.data() : nullptr))) return st;
         acc.device_ms += st1.device_ms; acc.playouts += st1.playouts; acc.moves += st1.moves;
         acc.rng_draws += st1.rng_draws; acc.kernel_launches += st1.kernel_launches;
-        const double cnsv = std::pow(2.0, avrg_win * 0.01);  // index_cnsv = 0.01, AgentGo.cpp:25,99
+        const double index_c = cfg.index_c;
+        const double cnsv = std::pow(2.0, avrg_win * cfg.index_cnsv);    // AgentGo.cpp:25,99
         // AMAF terms (:86-94,:329-338): decay table over the step of the first play.  The table
         // depends on the number of stones after the candidate is played, so the marks were
         // accumulated per distinct stone count; index_amaf_* defaults of :21-24, index_c = 1.
@@ -465,8 +480,8 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
             for (int k = 0; k < amaf_classes(); k++) {
                 const int64_t* A = amaf.data() + (size_t)k * AGB_AMAF_WORDS(n);
                 const int num_piece = amaf_class_stones()[k];
-                const double num_a = 1.0 / (40.0 - (39.0 / 180) * num_piece);
-                const double num_b = 0.3 - (0.3 / 180) * num_piece;
+                const double num_a = 1.0 / (cfg.index_amaf_a1 - cfg.index_amaf_a2 * num_piece);      // :87
+                const double num_b = cfg.index_amaf_b1 - cfg.index_amaf_b2 * num_piece;              // :88
                 double tab[AGB_AMAF_RANGE];
                 for (int t = 0; t < AGB_AMAF_RANGE; t++) {
                     double v = 1 - std::pow(num_a * t, num_b);
@@ -477,7 +492,7 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
                 for (int q = 0; q < NN; q++) {
                     double a1 = 0, a2 = 0;
                     for (int sidx = 2; sidx <= AGB_AMAF_RANGE; sidx++) {
-                        const double t = 100.0 * tab[sidx - 1];
+                        const double t = 100.0 * tab[sidx - 1] * index_c;
                         a1 += t * ((double)A[((size_t)(0 * 2 + 0) * S + sidx) * NN + q] + cnsv * (double)A[((size_t)(0 * 2 + 1) * S + sidx) * NN + q]);
                         a2 -= t * ((double)A[((size_t)(1 * 2 + 0) * S + sidx) * NN + q] + cnsv * (double)A[((size_t)(1 * 2 + 1) * S + sidx) * NN + q]);
                     }
@@ -491,8 +506,10 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
         double best = 0;
         int c = 0;
         last_marks.assign((size_t)n * n, 0.0);
-        const int bonus_a = (int)((double)P_cand * 1000.0);   // int(numset*index_a), :95, index_a = 1000 (:18)
-        const int bonus_b = (int)((double)P_cand * 1.0);      // int(numset*index_b), :96, index_b = 1 (:19)
+        // int(numset*index_a), int(numset*index_b) (:95-96); 64 bits: the reference's numset is 150, here
+        // the playouts per candidate are the caller's
+        const int64_t bonus_a = (int64_t)((double)P_cand * cfg.index_a);
+        const int64_t bonus_b = (int64_t)((double)P_cand * cfg.index_b);
         for (int i = 0; i < n; i++)
             for (int j = 0; j < n; j++) {
                 const bool is_cand = c < C && cand[2 * c] == i && cand[2 * c + 1] == j;
@@ -504,7 +521,7 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
                         mark = (double)(ua * bonus_a + ub * bonus_b);
                     }
                     // total_mark gets every score once (:339) and mc again (:653)
-                    mark += 2.0 * 100.0 * ((double)csp[c] + cnsv * (double)csn[c]);
+                    mark += 2.0 * 100.0 * index_c * ((double)csp[c] + cnsv * (double)csn[c]);
                     c++;
                 }
                 if (!board.is_eligible(colour, i, j)) { last_marks[(size_t)i * n + j] = mark; continue; }

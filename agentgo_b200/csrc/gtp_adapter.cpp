@@ -57,13 +57,24 @@ bool GTPAdapter::HandleLine(const std::string& line, std::ostream& out) {
             out << "? " << "unknown command : " << buf << "\n\n" << std::flush;
             return true;
         }
+        move_error.clear();
         played = onMove(isW, a, b);
+        if (!move_error.empty()) {
+            // the engine could not produce a move (CUDA error, move-cap fault, no device): that is a
+            // failure, not a pass — the reply is GTP's failure line and the board stays as it was
+            out << "? " << move_error << "\n\n" << std::flush;
+            return true;
+        }
         if (played) {
+            if (agb_play(eng, isW ? AGB_WHITE : AGB_BLACK, a, b) != AGB_OK) {
+                out << "? " << "genmove produced " << GaIntToChar(a) << b + 1 << " which cannot be played: "
+                    << agb_last_error(eng) << "\n\n" << std::flush;
+                return true;
+            }
             onMoved(isW, a, b);
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
             avgtime = (avgtime * times + ms) / (times + 1);
             times++;
-            agb_play(eng, isW ? AGB_WHITE : AGB_BLACK, a, b);
             out << "= " << GaIntToChar(a) << b + 1 << "\n\n" << std::flush;
         } else {
             out << "= " << "pass" << "\n\n" << std::flush;
@@ -132,13 +143,18 @@ void MyGame::onClear() {
     for (agb_engine* p : peers) agb_clear_board(p);
 }
 
-void MyGame::onPlay(int isW, int a, int b) {
-    for (agb_engine* p : peers) agb_play(p, isW + 1, a, b);
+// the peers mirror the first engine's board; one that cannot follow would play another game
+static void mirror(const std::vector<agb_engine*>& peers, int colour, int a, int b) {
+    for (agb_engine* p : peers)
+        if (agb_play(p, colour, a, b) != AGB_OK) {
+            fprintf(stderr, "a peer engine refused %d %d: %s\n", a, b, agb_last_error(p));
+            exit(1);
+        }
 }
 
-void MyGame::onMoved(int isW, int a, int b) {
-    for (agb_engine* p : peers) agb_play(p, isW + 1, a, b);
-}
+void MyGame::onPlay(int isW, int a, int b) { mirror(peers, isW + 1, a, b); }
+
+void MyGame::onMoved(int isW, int a, int b) { mirror(peers, isW + 1, a, b); }
 
 // MyGame::onMove (AgentGo.cpp:449-693): avrg_win from root playouts, the candidate filter,
 // playouts per candidate, argmax — all inside agb_genmove, which also holds the 13x13 opening
@@ -150,17 +166,30 @@ bool MyGame::onMove(int isW, int& a, int& b) {
     const unsigned long long sd = seed + 2ull * (unsigned long long)step;
     // every engine of a multi-GPU group evaluates its shard of the same genmove; the NCCL hook
     // inside sums the counters, so all of them return the same move
+    struct Res { int st, row, col, pass; };
+    std::vector<Res> pres(peers.size(), Res{0, -1, -1, 1});
     std::vector<std::thread> th;
-    for (agb_engine* p : peers)
-        th.emplace_back([=]() {
-            int r = -1, c = -1, ps = 1;
-            agb_genmove(p, isW + 1, P_cand, P_root, sd, &r, &c, &ps, nullptr);
+    for (size_t i = 0; i < peers.size(); i++)
+        th.emplace_back([=, &pres]() {
+            Res& r = pres[i];
+            r.st = agb_genmove(peers[i], isW + 1, P_cand, P_root, sd, &r.row, &r.col, &r.pass, nullptr);
         });
     const int st = agb_genmove(eng, isW + 1, P_cand, P_root, sd, &row, &col, &is_pass, &last);
     for (std::thread& t : th) t.join();
     if (st != AGB_OK) {
+        move_error = std::string("genmove failed: ") + agb_last_error(eng);
         fprintf(stderr, "agb_genmove failed: %s\n", agb_last_error(eng));
         return false;
+    }
+    for (size_t i = 0; i < peers.size(); i++) {
+        if (pres[i].st != AGB_OK) {
+            move_error = std::string("genmove failed on a peer engine: ") + agb_last_error(peers[i]);
+            return false;
+        }
+        if (pres[i].pass != is_pass || (!is_pass && (pres[i].row != row || pres[i].col != col))) {
+            move_error = "the engines of the group disagree on the move";
+            return false;
+        }
     }
     if (is_pass) return false;
     a = row;

@@ -20,6 +20,7 @@ protected:
     float komi;           // stored, never read (GTPAdapter.cpp:120-124), as in the reference
     double avgtime;       // running mean of genmove wall time in ms (GO_TIME_STAT, GTPAdapter.cpp:62-73)
     long times;
+    std::string move_error;   // set by onMove when no move could be produced: the reply is "? <text>", not "= pass"
 
 private:
     virtual void onClear() = 0;

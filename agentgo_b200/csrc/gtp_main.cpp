@@ -6,7 +6,10 @@
 //               [--amaf] [--static] [--book] [--reference-policy]
 //               [--selfplay [--max-moves K]]
 //               [--match G [--white-playouts P] [--white-policy flat|reference]]
+//               [index_a index_b index_c amaf_a1 amaf_a2 amaf_b1 amaf_b2 cnsv]
 //
+//   eight numbers       the reference's own command line (AgentGo.cpp:709-719): the tunables of the static marks,
+//                       the playout term, the AMAF decay table and cnsv (agb_config::index_*)
 //   --playouts P        playouts per candidate (reference: numset = 150, AgentGo.cpp:85)
 //   --total-playouts M  fixed budget per genmove, split evenly over the candidates
 //   --root-playouts R   testAvrgWin playouts (reference: 500, AgentGo.cpp:413)
@@ -42,6 +45,7 @@ int main(int argc, char** argv) {
     bool selfplay = false;
     int max_moves = 800, gpus = 1, match_games = 0, white_policy = -1;
     long long white_P = -1;
+    std::vector<double> positional;
     for (int i = 1; i < argc; i++) {
         const std::string a = argv[i];
         auto next = [&](const char* name) -> const char* {
@@ -68,7 +72,19 @@ int main(int argc, char** argv) {
             const std::string k = next("--kernel");
             cfg.kernel = k == "thread" ? AGB_KERNEL_THREAD : (k == "warp" ? AGB_KERNEL_WARP : (k == "group8" ? AGB_KERNEL_GROUP8 :
                          (k == "group16" ? AGB_KERNEL_GROUP16 : (k == "group32" ? AGB_KERNEL_GROUP32 : AGB_KERNEL_AUTO))));
+        } else if (a.size() >= 1 && (isdigit((unsigned char)a[0]) || ((a[0] == '-' || a[0] == '.') && a.size() > 1 && a[1] != '-'))) {
+            positional.push_back(atof(a.c_str()));
         } else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
+    }
+    // the reference's own command line: exactly eight doubles (AgentGo.cpp:709-719, `if (argc == 9)`)
+    if (positional.size() == 8) {
+        cfg.index_a = positional[0]; cfg.index_b = positional[1]; cfg.index_c = positional[2];
+        cfg.index_amaf_a1 = positional[3]; cfg.index_amaf_a2 = positional[4];
+        cfg.index_amaf_b1 = positional[5]; cfg.index_amaf_b2 = positional[6]; cfg.index_cnsv = positional[7];
+    } else if (!positional.empty()) {
+        fprintf(stderr, "expected the reference's eight tunables (index_a index_b index_c amaf_a1 amaf_a2 amaf_b1 amaf_b2 cnsv), got %zu numbers\n",
+                positional.size());
+        return 2;
     }
     // --gpus N: one engine per GPU (devices device..device+N-1), shard i of N, one NCCL communicator
     std::vector<agb_engine*> engines;

@@ -105,6 +105,15 @@ typedef struct agb_config {
     int genmove_book;    /* agb_genmove: 1 answers the first four calls after a clear_board from
                             the reference's 13x13 opening book (AgentGo.cpp:468-572); ignored on
                             other board sizes (the book is made of 13x13 literals)            */
+    /* The eight tunables of the reference's command line (AgentGo.cpp:18-25 defaults, :709-719
+     * argv[1..8]; the parameters its GA tuner searches).  agb_default_config sets the defaults.
+     *   index_a, index_b      static pattern marks: bonus_a = int(P*index_a), bonus_b = int(P*index_b) (:95-96)
+     *   index_c               scale of every playout term of the mark (:332,335,339,340)
+     *   index_amaf_a1..b2     AMAF decay table: 1 - (k / (a1 - a2*stones)) ^ (b1 - b2*stones)   (:87-94)
+     *   index_cnsv            cnsv = 2 ^ (avrg_win * index_cnsv), the weight of losing playouts (:99) */
+    double index_a, index_b, index_c;
+    double index_amaf_a1, index_amaf_a2, index_amaf_b1, index_amaf_b2;
+    double index_cnsv;
 } agb_config;
 /* amaf + static + book = the complete MyGame::onMove of the reference */
 

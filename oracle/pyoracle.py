@@ -234,6 +234,8 @@ class RefGame:
             lib.orc_gm_static_mark.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64]
             lib.orc_gm_static_mark.restype = C.c_double
             lib.orc_gm_calc_result.argtypes = [C.c_void_p]
+            if hasattr(lib, "orc_gm_set_tunables"):
+                lib.orc_gm_set_tunables.argtypes = [dp]
             _libs[key] = lib
         self.lib = _libs[key]
         self.h = self.lib.orc_gm_new()
@@ -274,6 +276,14 @@ class RefGame:
         moved = self.lib.orc_gm_genmove(self.h, colour, seed_base, C.byref(row), C.byref(col),
                                         *[t[k].ctypes.data_as(dp) for k in ("total_mark", "mc", "amaf1", "amaf2")])
         return ((row.value, col.value) if moved else None), t
+
+    DEFAULT_TUNABLES = (1000.0, 1.0, 1.0, 40.0, 39. / 180, 0.3, 0.3 / 180, 0.01)    # AgentGo.cpp:18-25
+
+    def set_tunables(self, v=None):
+        """the eight doubles of the reference's command line (AgentGo.cpp:709-719); they are globals of
+        the reference, so this holds for every RefGame of the process until it is called again"""
+        arr = (C.c_double * 8)(*[float(x) for x in (v or self.DEFAULT_TUNABLES)])
+        self.lib.orc_gm_set_tunables(arr)
 
     def calc_result(self):
         """CalcResults of the match harness (GeneHatchery.cpp:393-436): black - white."""

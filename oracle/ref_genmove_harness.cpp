@@ -40,6 +40,12 @@ int orc_gm_play(void* vg, int colour, int row, int col) {
     g->onPlay(colour - 1, row, col);
     return 0;
 }
+/* the eight tunables of the reference's command line (AgentGo.cpp:18-25, set from argv at :709-719) */
+void orc_gm_set_tunables(const double* v) {
+    index_a = v[0]; index_b = v[1]; index_c = v[2];
+    index_amaf_a1 = v[3]; index_amaf_a2 = v[4]; index_amaf_b1 = v[5]; index_amaf_b2 = v[6];
+    index_cnsv = v[7];
+}
 int orc_gm_step(void* vg) { return ((MyGame*)vg)->step; }
 void orc_gm_set_step(void* vg, int step) { ((MyGame*)vg)->step = step; }
 

@@ -42,6 +42,31 @@ def test_genmove_matches_reference_live(built_lib):
     check(e, 1, 424242, want_mv, t["total_mark"])
 
 
+@pytest.mark.skipif(not po.genmove_ref_available(), reason="oracle/_ref/liboracle_ref_genmove_13.so not built")
+def test_genmove_with_other_tunables_matches_reference(built_lib):
+    """The eight tunables of the reference's command line (AgentGo.cpp:18-25,709-719), set to something
+    else than the defaults on both sides: same move, same total_mark table."""
+    tun = (700.0, 3.0, 0.5, 35.0, 0.15, 0.45, 0.001, 0.03)
+    moves = po.OracleBoard(13, "reference").random_game(1, 70, 2718)
+    ref = po.RefGame().replay(moves)
+    if not hasattr(ref.lib, "orc_gm_set_tunables"):
+        pytest.skip("oracle/_ref was built before the tunables setter existed")
+    ref.step = 9
+    ref.set_tunables(tun)
+    try:
+        want_mv, t = ref.genmove(2, 99991)
+    finally:
+        ref.set_tunables(None)
+    e = ag.Engine(13, genmove_amaf=1, genmove_static=1, genmove_book=1, tunables=tun).replay(moves)
+    e.genmove_step = 9
+    check(e, 2, 99991, want_mv, t["total_mark"])
+    # and the defaults are not what was just compared
+    e2 = ag.Engine(13, genmove_amaf=1, genmove_static=1, genmove_book=1).replay(moves)
+    e2.genmove_step = 9
+    e2.genmove(2, 150, 500, 99991)
+    assert not np.allclose(e2.last_marks(), t["total_mark"], rtol=1e-6)
+
+
 def test_game_opening_then_playouts(built_lib):
     """A game from the empty board: four book moves per engine, then the Monte-Carlo branch."""
     e = ag.Engine(13, genmove_amaf=1, genmove_static=1, genmove_book=1)

@@ -35,6 +35,24 @@ def test_wire_format_without_gpu(built_lib):
     assert out == exp
 
 
+def test_failed_genmove_is_an_error_not_a_pass(built_lib):
+    """An engine that cannot run playouts (no device: --device -1; on a GPU a CUDA error or the move
+    cap) answers GTP's failure line and leaves the board alone; it used to answer `= pass`."""
+    out = gtp(["boardsize 9", "play b E5", "genmove w", "play w E5", "quit"], "--device", "-1")
+    replies = [l for l in out.split("\n\n") if l]
+    assert replies[0] == "=" and replies[1] == "= "
+    assert replies[2].startswith("? genmove failed: ") and "no CPU fallback" in replies[2]
+    assert replies[3] == "? unknown command : play w E5"     # E5 still holds the black stone
+
+
+def test_reference_command_line_tunables(built_lib):
+    """agentgo_gtp takes the reference's own command line: eight doubles (AgentGo.cpp:709-719)."""
+    out = gtp(["name", "quit"], "--device", "-1", "1000", "1", "1", "40", "0.2166", "0.3", "0.00166", "0.01")
+    assert out.startswith("= AgentGo")
+    r = subprocess.run([GTP, "--device", "-1", "1", "2", "3"], input="quit\n", capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "eight tunables" in r.stderr
+
+
 def test_coordinates_skip_letter_i(built_lib):
     # GaCharToInt / GaIntToChar (GTPAdapter.cpp:19-20): a..h -> 0..7, j -> 8; the LETTER is the row
     e = ag.Engine(19, device=-1)
