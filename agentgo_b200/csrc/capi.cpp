@@ -84,6 +84,7 @@ const char* agb_last_error(const agb_engine* h) {
 int agb_boardsize(agb_engine* h, int n) {
     if (!h) return AGB_ERR_INVALID;
     if (!agb::HostBoard::size_supported(n)) return h->e->fail(AGB_ERR_INVALID, "unsupported board size");
+    if (h->e->busy()) return h->e->fail(AGB_ERR_STATE, "a launch is in flight: finish it before changing the position");
     h->e->board.reset(n);
     h->e->genmove_step = 0;
     return AGB_OK;
@@ -91,6 +92,7 @@ int agb_boardsize(agb_engine* h, int n) {
 
 int agb_clear_board(agb_engine* h) {
     if (!h) return AGB_ERR_INVALID;
+    if (h->e->busy()) return h->e->fail(AGB_ERR_STATE, "a launch is in flight: finish it before changing the position");
     h->e->board.clear();
     h->e->genmove_step = 0;                 /* MyGame::onClear, AgentGo.cpp:377 */
     return AGB_OK;
@@ -98,6 +100,7 @@ int agb_clear_board(agb_engine* h) {
 
 int agb_play(agb_engine* h, int colour, int row, int col) {
     if (!h) return AGB_ERR_INVALID;
+    if (h->e->busy()) return h->e->fail(AGB_ERR_STATE, "a launch is in flight: finish it before changing the position");
     int st = h->e->board.play(colour, row, col);
     if (st == -1) return h->e->fail(AGB_ERR_INVALID, "illegal colour or coordinates");
     if (st == -2) return h->e->fail(AGB_ERR_OCCUPIED, "point occupied");
@@ -107,6 +110,7 @@ int agb_play(agb_engine* h, int colour, int row, int col) {
 int agb_pass(agb_engine* h, int colour) {
     if (!h) return AGB_ERR_INVALID;
     if (colour != AGB_BLACK && colour != AGB_WHITE) return h->e->fail(AGB_ERR_INVALID, "bad colour");
+    if (h->e->busy()) return h->e->fail(AGB_ERR_STATE, "a launch is in flight: finish it before changing the position");
     h->e->board.pass(colour);
     return AGB_OK;
 }

@@ -232,24 +232,32 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
 int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats,
                    int64_t* amaf) {
     if (!in_flight_) return fail(AGB_ERR_STATE, "no launch in flight");
+    // everything that can be refused is refused before anything is enqueued behind the kernel
+    if (amaf && !want_amaf_) return fail(AGB_ERR_STATE, "the launch in flight did not record AMAF marks");
     in_flight_ = false;
     AGB_CUDA(cudaSetDevice(cfg.device));
     const int S = n_starts_;
-    // snapshot the shard-local stats before any collective touches the counters
     const int T = stride_;      // the counter table is [3][T], T >= S
+    // an error from here on leaves work queued on the stream that may still write the caller's
+    // buffers: wait for it before returning
+    auto bail = [&](int status, const char* msg) {
+        cudaStreamSynchronize(stream_);
+        return fail(status, msg);
+    };
+    // snapshot the shard-local stats before any collective touches the counters
     const size_t need = sizeof(long long) * 3 * (size_t)T + kSmallWords * sizeof(unsigned long long);
     if (cap_pinned_ < need) {
         if (h_pinned_) cudaFreeHost(h_pinned_);
         h_pinned_ = nullptr; cap_pinned_ = 0;
-        AGB_CUDA(cudaMallocHost(&h_pinned_, need));
+        if (cudaMallocHost(&h_pinned_, need) != cudaSuccess) return bail(AGB_ERR_NOMEM, "cudaMallocHost failed");
         cap_pinned_ = need;
     }
     if (allreduce_) {
         int r = allreduce_(allreduce_ctx_, d_counters_, 3 * T, (void*)stream_);
-        if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
+        if (r) return bail(AGB_ERR_CUDA, "allreduce callback failed");
         if (want_amaf_) {
             r = allreduce_(allreduce_ctx_, d_amaf_, AGB_AMAF_WORDS(board.n()) * amaf_classes(), (void*)stream_);
-            if (r) return fail(AGB_ERR_CUDA, "allreduce callback failed");
+            if (r) return bail(AGB_ERR_CUDA, "allreduce callback failed");
         }
     }
     // device time of the evaluation = kernel (+ collective), stream ordered
@@ -261,7 +269,6 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
     if (diffs && want_diffs_ && !(shard_units_ && cfg.shard_count > 1))
         AGB_CUDA(cudaMemcpyAsync(diffs, d_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P_, cudaMemcpyDeviceToHost, stream_));
     if (amaf) {
-        if (!want_amaf_) return fail(AGB_ERR_STATE, "the launch in flight did not record AMAF marks");
         AGB_CUDA(cudaMemcpyAsync(amaf, d_amaf_, sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n()) * (size_t)amaf_classes(),
                                  cudaMemcpyDeviceToHost, stream_));
     }
@@ -458,17 +465,22 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
             if (board.is_candidate(colour, i, j)) { cand.push_back((int16_t)i); cand.push_back((int16_t)j); }
     const int C = (int)cand.size() / 2;
     *is_pass = 1; *row = -1; *col = -1;
-    if (C > 0) {
+    {
+        // (no candidate survives the filter: nothing is played out, but the reference still takes the
+        // first point that is empty and neither a true eye, a suicide nor the ko point — those the filter
+        // dropped for checkNoSense compete with mark 0, :647-676)
         std::vector<int64_t> cw(C), csp(C), csn(C);
-        if (P_cand < 0) P_cand = (-P_cand + C - 1) / C;      // fixed budget per genmove, split over candidates
-        const bool use_amaf = cfg.genmove_amaf != 0 && cfg.kernel != AGB_KERNEL_THREAD;
+        if (P_cand < 0) P_cand = C > 0 ? (-P_cand + C - 1) / C : -P_cand;      // fixed budget per genmove, split over candidates
+        const bool use_amaf = C > 0 && cfg.genmove_amaf != 0 && cfg.kernel != AGB_KERNEL_THREAD;
         std::vector<int64_t> amaf;
-        st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false, use_amaf, use_amaf);
-        if (st) return st;
-        if (use_amaf) amaf.resize((size_t)AGB_AMAF_WORDS(n) * (size_t)amaf_classes());
-        if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1, use_amaf ? amaf.data() : nullptr))) return st;
-        acc.device_ms += st1.device_ms; acc.playouts += st1.playouts; acc.moves += st1.moves;
-        acc.rng_draws += st1.rng_draws; acc.kernel_launches += st1.kernel_launches;
+        if (C > 0) {
+            st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false, use_amaf, use_amaf);
+            if (st) return st;
+            if (use_amaf) amaf.resize((size_t)AGB_AMAF_WORDS(n) * (size_t)amaf_classes());
+            if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1, use_amaf ? amaf.data() : nullptr))) return st;
+            acc.device_ms += st1.device_ms; acc.playouts += st1.playouts; acc.moves += st1.moves;
+            acc.rng_draws += st1.rng_draws; acc.kernel_launches += st1.kernel_launches;
+        }
         const double index_c = cfg.index_c;
         const double cnsv = std::pow(2.0, avrg_win * cfg.index_cnsv);    // AgentGo.cpp:25,99
         // AMAF terms (:86-94,:329-338): decay table over the step of the first play.  The table

@@ -60,6 +60,7 @@ public:
     void set_allreduce(AllreduceFn fn, void* ctx) { allreduce_ = fn; allreduce_ctx_ = ctx; }
     void set_allgather(AllgatherFn fn, void* ctx) { allgather_ = fn; allgather_ctx_ = ctx; }
     int fail(int status, const std::string& msg) { err = msg; return status; }
+    bool busy() const { return in_flight_; }     // between *_launch and *_finish: the position must not change
 
 private:
     Engine() : board(13) {}

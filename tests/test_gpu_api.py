@@ -170,7 +170,7 @@ def _oracle_genmove(ob, n, colour, P_cand, P_root, seed_base, use_amaf=False, mo
                 m = marks.get((i, j), 0.0) + amaf12[i * n + j]
                 if best is None or m > best:
                     best, arg = m, (i, j)
-    return arg if cands else None
+    return arg      # also without candidates: the first eligible point competes with mark 0 (AgentGo.cpp:647-676)
 
 
 def test_genmove_matches_oracle_restatement(built_lib):
