@@ -83,6 +83,7 @@ extern "C" long long emu_group_playouts(int n, int lanes, const uint32_t* moves,
     a.jump_bytes = jb.data();
     a.descs = &d;
     a.n_starts = 1;
+    a.counter_stride = 1;
     a.P = P;
     a.seed_base = seed_base;
     a.shard_rank = 0; a.shard_count = 1;
