@@ -1,5 +1,5 @@
 // diag.cu — live micro-benchmarks of the two machine rates that bound the playout kernels:
-// INT32 issue (IADD3/LOP3 on the alu pipe + IMAD on the fma pipe) and shared-memory bandwidth.
+// INT32 issue (LOP3 on the alu pipe + IMAD on the fma pipe) and shared-memory bandwidth.
 // the path is SM integer-issue / shared-memory bound, not HBM or tensor, and the
 // peaks must be MEASURED at the clock the GPU actually runs at.
 #include <cuda_runtime.h>
@@ -11,24 +11,37 @@ namespace {
 
 constexpr int kIters = 4096;
 
-// 8 independent chains per thread, alternating alu-pipe (LOP3/IADD3) and fma-pipe (IMAD) ops
+// 8 independent chains per thread.  The instruction mix is pinned with inline PTX (the compiler moves
+// plain adds between the two pipes as it likes):
+//   mixed:    lop3 on the alu pipe and mad.lo on the fma pipe, one to one — each pipe takes a warp
+//             instruction every second cycle, together they fill the issue slot of every cycle, which
+//             is the integer ceiling of the SM (128 lane-ops per clock);
+//   alu only: lop3 alone — the alu pipe's own ceiling (64 lane-ops per clock per SM).
+// profiles/r02_peak_kernels.txt holds the ncu capture that shows which pipe each one saturates.
 __global__ void __launch_bounds__(1024) int_peak_kernel(uint32_t* out, uint32_t seed, int mixed) {
     uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3u, a2 = a0 ^ 0x1234u, a3 = a0 + 77u;
     uint32_t b0 = a0 * 5u, b1 = a0 * 7u + 1u, b2 = a0 ^ 0xabcdefu, b3 = a0 + 99u;
     const uint32_t k = seed | 1u;
+#define AGB_LOP(d, x, y) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(d) : "r"(x), "r"(y))
+#define AGB_MAD(d, x, y) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(d) : "r"(x), "r"(y))
     if (mixed) {
 #pragma unroll 8
         for (int i = 0; i < kIters; i++) {
-            a0 = (a0 ^ k) + b0; a1 = (a1 ^ k) + b1; a2 = (a2 ^ k) + b2; a3 = (a3 ^ k) + b3;     // LOP3 + IADD3
-            b0 = b0 * k + a0; b1 = b1 * k + a1; b2 = b2 * k + a2; b3 = b3 * k + a3;             // IMAD
+            AGB_LOP(a0, k, b0); AGB_MAD(b0, k, a0); AGB_LOP(a1, k, b1); AGB_MAD(b1, k, a1);
+            AGB_LOP(a2, k, b2); AGB_MAD(b2, k, a2); AGB_LOP(a3, k, b3); AGB_MAD(b3, k, a3);
+            AGB_LOP(a0, k, b1); AGB_MAD(b0, k, a1); AGB_LOP(a1, k, b2); AGB_MAD(b1, k, a2);
         }
     } else {
 #pragma unroll 8
         for (int i = 0; i < kIters; i++) {
-            a0 = (a0 ^ k) + b0; a1 = (a1 ^ k) + b1; a2 = (a2 ^ k) + b2; a3 = (a3 ^ k) + b3;
-            b0 = (b0 ^ a0) + k; b1 = (b1 ^ a1) + k; b2 = (b2 ^ a2) + k; b3 = (b3 ^ a3) + k;
+            AGB_LOP(a0, k, b0); AGB_LOP(b0, k, a0); AGB_LOP(a1, k, b1); AGB_LOP(b1, k, a1);
+            AGB_LOP(a2, k, b2); AGB_LOP(b2, k, a2); AGB_LOP(a3, k, b3); AGB_LOP(b3, k, a3);
+            AGB_LOP(a0, k, b1); AGB_LOP(b0, k, a1); AGB_LOP(a1, k, b2); AGB_LOP(b1, k, a2);
+            AGB_LOP(a2, k, b3); AGB_LOP(b2, k, a3); AGB_LOP(a3, k, b0); AGB_LOP(b3, k, a0);
         }
     }
+#undef AGB_LOP
+#undef AGB_MAD
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ b0 ^ b1 ^ b2 ^ b3;
 }
 
@@ -76,8 +89,8 @@ extern "C" int agb_measure_peaks(int device, double* int_ops_per_s, double* int_
             if (rep > 0 && ms < best) best = ms;
         }
         const double n_thr = (double)blocks * threads;
-        if (which == 0) res[0] = n_thr * kIters * 12.0 / (best * 1e-3);       // 4 LOP3 + 4 IADD3 + 4 IMAD
-        else if (which == 1) res[1] = n_thr * kIters * 16.0 / (best * 1e-3);  // 8 LOP3 + 8 IADD3
+        if (which == 0) res[0] = n_thr * kIters * 12.0 / (best * 1e-3);       // 6 LOP3 + 6 IMAD
+        else if (which == 1) res[1] = n_thr * kIters * 16.0 / (best * 1e-3);  // 16 LOP3
         else res[2] = n_thr * kIters * 4.0 / (best * 1e-3);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);

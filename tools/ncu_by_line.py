@@ -2,7 +2,9 @@
 """Join an ncu report's per-SASS-instruction counters with nvdisasm line info and aggregate by
 CUDA source line (inlined code is attributed to the line where it was written).
 
-usage: tools/ncu_by_line.py <report.ncu-rep> <lib.so> <kernel-substring> [top]
+usage: tools/ncu_by_line.py <report.ncu-rep> <lib.so> <kernel-substring> [top] [--smem]
+--smem: rank the lines by shared-memory wavefronts instead and show, per line, the wavefronts
+the accesses needed, the ideal number and the excess (bank conflicts).
 Needs -lineinfo at compile time.  Works offline (no GPU)."""
 import csv
 import collections
@@ -14,8 +16,10 @@ import tempfile
 
 
 def main():
-    rep, lib, kern = sys.argv[1], sys.argv[2], sys.argv[3]
-    top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    smem_mode = "--smem" in sys.argv
+    argv = [a for a in sys.argv if a != "--smem"]
+    rep, lib, kern = argv[1], argv[2], argv[3]
+    top = int(argv[4]) if len(argv) > 4 else 40
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
     lines = []   # (file, line) per instruction of the kernel, in order
@@ -60,6 +64,7 @@ def main():
     if len(data) != len(lines):
         sys.stderr.write("warning: %d ncu rows vs %d disassembled instructions\n" % (len(data), len(lines)))
     inst = collections.Counter(); smp = collections.Counter(); static = collections.Counter()
+    wav = collections.Counter(); exc = collections.Counter(); ideal = collections.Counter()
     stall_cols = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
     stalls = collections.defaultdict(collections.Counter)
     for k in range(n):
@@ -67,6 +72,10 @@ def main():
         inst[key] += int(data[k][ix["Instructions Executed"]])
         smp[key] += int(data[k][ix["# Samples"]])
         static[key] += 1
+        if "L1 Wavefronts Shared" in ix:
+            wav[key] += int(data[k][ix["L1 Wavefronts Shared"]] or 0)
+            exc[key] += int(data[k][ix["L1 Wavefronts Shared Excessive"]] or 0)
+            ideal[key] += int(data[k][ix["L1 Wavefronts Shared Ideal"]] or 0)
         for h in stall_cols:
             v = data[k][ix[h]]
             if v and v != "0":
@@ -88,6 +97,17 @@ def main():
         s = src_cache[f]
         return s[l - 1].strip()[:90] if 0 < l <= len(s) else ""
 
+    if smem_mode:
+        tw, te = sum(wav.values()), sum(exc.values())
+        print("shared-memory wavefronts %d, ideal %d, excessive (bank conflicts) %d = %.1f%% of all wavefronts" %
+              (tw, sum(ideal.values()), te, 100.0 * te / max(1, tw)))
+        print("%7s %7s %9s  %-22s %s" % ("wavef%", "excess%", "exc/ideal", "where", "source"))
+        for key, v in sorted(wav.items(), key=lambda kv: -kv[1])[:top]:
+            if v == 0:
+                break
+            print("%7.2f %7.2f %9.2f  %-22s %s" % (100.0 * v / tw, 100.0 * exc[key] / max(1, te), exc[key] / max(1, ideal[key]),
+                                                    "%s:%d" % key, src(key)))
+        return
     print("%6s %6s %6s  %-22s %s" % ("inst%", "smp%", "static", "where", "source / top stalls"))
     for key, v in sorted(smp.items(), key=lambda kv: -kv[1])[:top]:
         st = ", ".join("%s %d%%" % (h[6:], 100 * c / max(1, smp[key])) for h, c in stalls[key].most_common(3))
