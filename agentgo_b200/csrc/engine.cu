@@ -106,7 +106,7 @@ Engine::~Engine() {
     cudaSetDevice(cfg.device);
     if (stream_) cudaStreamSynchronize(stream_);
     cudaFree(d_starts_); cudaFree(d_descs_); cudaFree(d_counters_); cudaFree(d_diffs_);
-    cudaFree(d_gather_); cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_amaf_);
+    cudaFree(d_gather_); cudaFree(d_elist_); cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_amaf_);
     if (h_pinned_) cudaFreeHost(h_pinned_);
     if (h_stage_) cudaFreeHost(h_stage_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -197,6 +197,9 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
             jump_bytes_lanes_ = group_lanes;
         }
         a.jump_bytes = (const uint4*)d_jump_bytes_;
+        // the empty-point arrays of the resident playouts (global memory, kernel_args.h)
+        if ((st = ensure(&d_elist_, &cap_elist_, (size_t)sm_count_ * kGroupMaxPlayoutsPerSm * kGroupElistCap * sizeof(uint16_t)))) return st;
+        a.elist_scratch = (uint16_t*)d_elist_;
     }
     a.descs = (const StartDesc*)d_descs_;
     a.n_starts = S;

@@ -73,6 +73,7 @@ private:
     void* d_starts_ = nullptr; size_t cap_starts_ = 0;
     void* d_jump_ = nullptr;             // JumpTable (TinyMT32 T^16), built at create time
     void* d_jump_bytes_ = nullptr; size_t cap_jump_bytes_ = 0;   // JumpBytes of the group kernel
+    void* d_elist_ = nullptr; size_t cap_elist_ = 0;   // group kernel: empty-point arrays of the resident playouts
     int jump_bytes_lanes_ = 0;           // lanes per playout d_jump_bytes_ was built for
     void* h_stage_ = nullptr; size_t cap_stage_ = 0;   // pinned staging of the start positions + descriptors
     void* d_descs_ = nullptr; size_t cap_descs_ = 0;

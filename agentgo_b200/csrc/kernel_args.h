@@ -43,7 +43,7 @@ struct PaddedPosition {
 //   bits 0-1 colour | bits 2-10 A | bits 11-19 next | bits 21-31 F
 //        stone:  A = root of its string, next = next stone of the string (511 = end),
 //                F = pseudo-liberties at the root stone / the string's last stone at its SECOND stone
-//        empty:  A = the point itself, next = slot of the point in `elist`, F = 1
+//        empty:  A = the point itself, bits 11-20 = slot of the point in `elist`, F = 1
 //        border: A = the point itself, colour 3, F = 1
 // (A sits at bit 2 so that `w & 0x7fc` is the byte offset of the root's word; F is at the top so
 // that the liberties of a root are one shift away; F = 1 on points without a stone makes "liberties
@@ -58,7 +58,11 @@ AGB_HD constexpr uint32_t stone(uint32_t root, uint32_t next, uint32_t f, uint32
 AGB_HD constexpr uint32_t empty(uint32_t self, uint32_t slot) { return (self << kAShift) | (slot << kNextShift) | kOne; }
 AGB_HD constexpr uint32_t border(uint32_t self) { return 3u | (self << kAShift) | kOne; }
 }  // namespace gw
-constexpr int group_elist_cap(int n) { return n * n + 15; }    // entries in shared memory; compacted when full
+// entries of a playout's empty-point array in the group kernel; it lives in GLOBAL memory (L2): it is
+// read by complex mode and compaction only, and 752 B of shared memory per playout buy five more
+// warps per SM.  1024 = what the 10-bit slot field of an empty point can name.
+constexpr int kGroupElistCap = 1024;
+constexpr int kGroupMaxPlayoutsPerSm = 128;
 struct GroupPosition {
     uint32_t w[kMaxNP];
     uint32_t elist_w[(kMaxNN + 1) / 2];    // n_el 16-bit entries
@@ -95,6 +99,7 @@ struct KernelArgs {
     const GroupPosition* gstarts;   // [n_starts] device (group kernel)
     const JumpTable* jump;      // device (warp kernel)
     const uint4* jump_bytes;    // device (group kernel), JumpBytes for the launch's lanes per playout
+    uint16_t* elist_scratch;    // device (group kernel): kGroupElistCap entries per resident playout
     const StartDesc* descs;     // [n_starts] device
     int32_t n_starts;
     int64_t P;

@@ -10,12 +10,13 @@ template <class C, int WARPS, int BLOCKS_PER_SM>
 __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_group_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    grp::playout_group_body<C>(a, smem + (size_t)warp * C::warp_words, lane);
+    grp::playout_group_body<C>(a, smem + (size_t)warp * C::warp_words, lane, (int)blockIdx.x * WARPS + warp);
 }
 
 template <int N, int G, int WARPS, int BLOCKS_PER_SM>
 cudaError_t launch_g(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
     typedef grp::GCfg<N, G, kJumpSteps> C;
+    static_assert(WARPS * BLOCKS_PER_SM * C::NG <= kGroupMaxPlayoutsPerSm, "elist_scratch is sized for 128 playouts per SM");
     const size_t smem = (size_t)WARPS * C::warp_words * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(playout_group_kernel<C, WARPS, BLOCKS_PER_SM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -32,14 +33,14 @@ cudaError_t launch_g(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchIn
 }  // namespace
 
 cudaError_t launch_playout_group(int n, int lanes, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    // 8 lanes per playout: 76 playouts per SM (3 056 B each at 19x19) in one block of 19 warps, 104 registers;
-    // 16 lanes: 64 playouts in 32 warps of 64 registers; 32 lanes (the mapping of playout_warp.cu
-    // run through this code, for comparison): 32 playouts in 32 warps.
+    // 8 lanes per playout: 100 playouts per SM (2 304 B of shared memory each at 19x19) in one block of
+    // 25 warps, 80 registers; 16 lanes: 64 playouts in 32 warps of 64 registers; 32 lanes (the mapping
+    // of playout_warp.cu run through this code, for comparison): 32 playouts in 32 warps.
     if (lanes == 8) {
         switch (n) {
-            case 9: return launch_g<9, 8, 19, 1>(a, sm_count, s, info);
-            case 13: return launch_g<13, 8, 19, 1>(a, sm_count, s, info);
-            case 19: return launch_g<19, 8, 19, 1>(a, sm_count, s, info);
+            case 9: return launch_g<9, 8, 24, 1>(a, sm_count, s, info);
+            case 13: return launch_g<13, 8, 24, 1>(a, sm_count, s, info);
+            case 19: return launch_g<19, 8, 24, 1>(a, sm_count, s, info);
         }
     } else if (lanes == 16) {
         switch (n) {

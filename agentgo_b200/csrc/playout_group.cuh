@@ -31,9 +31,11 @@
 //    With A = own index on empty and border points the root of "whatever is next to a point" is
 //    one AND away with no case split (w & 0x7fc is even its byte offset), and equal roots mean
 //    the same string.
-//  * The empty-point list is the append-only array of the warp kernel (kernel_args.h), the rand()
-//    ring too, but smaller (R = 2*G*SEG entries), refilled whenever a phase is about to read past
-//    its end: state per playout 3.1 KB at 19x19, 72 playouts per SM.
+//  * The empty-point list is the append-only array of the warp kernel (kernel_args.h) — in GLOBAL
+//    memory (L2): only complex mode and compaction read it, all 32 lanes at a time, and the 752 B
+//    it took per playout were five warps per SM.  The rand() ring is smaller than the warp kernel's
+//    (R = 2*G*SEG entries) and refilled whenever a phase is about to read past its end.  State per
+//    playout in shared memory: 2 304 B at 19x19, 100 playouts = 25 warps per SM.
 //
 // Restates Board.cpp:68-177 (put), :293-339 (killSetNode), :341-411 (getRandomPiece), :413-478
 // (getRandomPieceComplex), :480-755 (predicates), :910-925 (countScore) and the pair loops of
@@ -65,12 +67,23 @@ constexpr uint32_t kResFlag = 0x8000u;     // elist entry: point is reserved in 
 AGB_DEV uint32_t fA(uint32_t w) { return (w >> gw::kAShift) & 511u; }
 AGB_DEV uint32_t offA(uint32_t w) { return w & kAMask; }                 // byte offset of the root's word
 AGB_DEV uint32_t fNext(uint32_t w) { return (w >> gw::kNextShift) & 511u; }
+AGB_DEV uint32_t fSlot(uint32_t w) { return (w >> gw::kNextShift) & 1023u; }         // empty point: its entry in elist
 AGB_DEV uint32_t fHp(uint32_t w) { return w >> gw::kFShift; }
 AGB_DEV uint32_t fCol(uint32_t w) { return w & 3u; }
 AGB_DEV bool isEmpty(uint32_t w) { return (w & 3u) == 0; }
 AGB_DEV uint32_t setA(uint32_t w, uint32_t a) { return (w & ~kAMask) | (a << gw::kAShift); }
 AGB_DEV uint32_t setNext(uint32_t w, uint32_t n) { return (w & ~kNextMask) | (n << gw::kNextShift); }
 AGB_DEV uint32_t setF(uint32_t w, uint32_t f) { return (w & ~kHpMask) | (f << gw::kFShift); }
+// the empty-point array lives in global memory and is handed from lane to lane: L2 accesses
+#ifdef AGB_EMU
+AGB_DEV uint32_t eld(const uint16_t* p) { return *p; }
+AGB_DEV void est(uint16_t* p, uint32_t v) { *p = (uint16_t)v; }
+AGB_DEV void est32(uint32_t* p, uint32_t v) { *p = v; }
+#else
+AGB_DEV uint32_t eld(const uint16_t* p) { return __ldcg(p); }
+AGB_DEV void est(uint16_t* p, uint32_t v) { __stcg(p, (unsigned short)v); }
+AGB_DEV void est32(uint32_t* p, uint32_t v) { __stcg(p, v); }
+#endif
 AGB_DEV uint32_t at(const uint32_t* w, uint32_t byte_off) {              // the word at a byte offset
     return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(w) + byte_off);
 }
@@ -81,10 +94,9 @@ struct GCfg {
     static constexpr int W = N + 2, NP = W * W, NN = N * N, NG = 32 / G;
     static constexpr int BATCH = G * SEG;           // draws per refill of one playout
     static constexpr int R = 2 * BATCH;             // ring entries
-    static constexpr int E = group_elist_cap(N);    // elist entries (kernel_args.h)
-    // shared-memory words of one playout: ring | board | elist, a multiple of 4 (the ring is
-    // written with 128-bit stores)
-    static constexpr int oRing = 0, oBoard = R / 2, oElist = oBoard + NP, oCbuf = oElist + (E + 1) / 2;
+    static constexpr int E = kGroupElistCap;        // elist entries, in global memory (kernel_args.h)
+    // shared-memory words of one playout: ring | board | cbuf, a multiple of 4
+    static constexpr int oRing = 0, oBoard = R / 2, oCbuf = oBoard + NP;
     static constexpr int words = ((oCbuf + G / 2 + 3) / 4) * 4;    // cbuf: G 16-bit entries, the candidates of a move
     static constexpr int warp_words = NG * words;
     static constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
@@ -222,46 +234,74 @@ AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams p
 
 // ---- bulk work, all 32 lanes for one group ------------------------------------------------------
 // Drop the dead entries of elist, keeping the order.  Entry k naming point c is alive iff c is
-// empty and its slot is k (a zeroed entry names the border point 0).  In place: a round reads 32
-// entries and then writes at or below where it read.  Returns the new number of entries.
+// empty and its slot is k (a zeroed entry names the border point 0).  In place: a pass reads 128
+// entries (the four loads are in flight together: the array lives in L2) and then writes at or
+// below where it read.  Returns the new number of entries.
 template <class C>
 AGB_NOINLINE int compact(uint32_t* w, uint16_t* elist, int n_el, int lane) {
     int out = 0;
 #pragma unroll 1
-    for (int base = 0; base < n_el; base += 32) {
-        const int k = base + lane;
-        const uint32_t c = k < n_el ? ((uint32_t)elist[k] & 0x1ffu) : 0u;
-        const uint32_t wc = w[c];
-        const bool alive = isEmpty(wc) && (int)fNext(wc) == k;
-        const unsigned m = __ballot_sync(kFull, alive);
-        __syncwarp();
-        if (alive) {
-            const int o = out + __popc(m & ((1u << lane) - 1u));
-            elist[o] = (uint16_t)c;
-            w[c] = gw::empty(c, (uint32_t)o);
+    for (int base = 0; base < n_el; base += 128) {
+        uint32_t c[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = base + 32 * u + lane;
+            c[u] = k < n_el ? (eld(elist + k) & 0x1ffu) : 0u;
         }
-        out += __popc(m);
+        __syncwarp();       // all of the pass is read before any of it is overwritten
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = base + 32 * u + lane;
+            const uint32_t wc = w[c[u]];
+            const bool alive = isEmpty(wc) && (int)fSlot(wc) == k;
+            const unsigned m = __ballot_sync(kFull, alive);
+            if (alive) {
+                const int o = out + __popc(m & ((1u << lane) - 1u));
+                est(elist + o, c[u]);
+                w[c[u]] = gw::empty(c[u], (uint32_t)o);
+            }
+            out += __popc(m);
+        }
     }
     __syncwarp();
     return out;
 }
 
 // Board::getRandomPieceComplex, Board.cpp:413-478, for one group.  Pass 1 (reserve flags, :419-433):
-// one lane per entry of elist, flagged in place.  Pass 2 (:445-470, the rnd-th unreserved point in
-// list order) counts 32 entries per round from the end of the array.  draw = the playout's next
-// rand() value; *used says whether it was consumed.
+// one lane per entry of elist.  Pass 2 (:445-470, the rnd-th unreserved point in list order) counts
+// 32 entries per round from the end of the array.  The first kKeep rounds of entries — all of them,
+// as a rule: complex mode means few empty points — stay in registers with their flags between the two
+// passes (64 entries), so the array (it lives in L2) is read once, all rounds in flight together, and not written;
+// entries beyond that are flagged in place.  draw = the playout's next rand() value; *used says
+// whether it was consumed.
 template <class C>
 AGB_NOINLINE int complex_pick(uint32_t* w, uint16_t* elist, int n_el, int spaces, uint32_t agent, int ko_key,
                               uint32_t draw, int lane, int* used) {
+    constexpr int kKeep = 2;
+    uint32_t ents[kKeep];
+#pragma unroll
+    for (int r = 0; r < kKeep; r++) {
+        const int k = 32 * r + lane;
+        ents[r] = k < n_el ? (eld(elist + k) & 0x1ffu) : 0u;                        // 0: a dead entry
+    }
     int reserved_total = 0;
+#pragma unroll
+    for (int r = 0; r < kKeep; r++) {
+        if (32 * r < n_el) {
+            // dead entries look at some point of the board; their result is dropped
+            const Ev e = eval_point<C::W, kEvRes>(w, agent, ents[r] ? (int)ents[r] : C::W + 1, ko_key);
+            const bool res = e.bad && ents[r] != 0;
+            if (res) ents[r] |= kResFlag;                                           // addReserve, :757-761
+            reserved_total += __popc(__ballot_sync(kFull, res));
+        }
+    }
 #pragma unroll 1
-    for (int base = 0; base < n_el; base += 32) {
+    for (int base = 32 * kKeep; base < n_el; base += 32) {
         const int k = base + lane;
-        const int ent = k < n_el ? (int)((uint32_t)elist[k] & 0x1ffu) : 0;          // 0: a dead entry
-        // dead entries look at some point of the board; their result is dropped
+        const int ent = k < n_el ? (int)(eld(elist + k) & 0x1ffu) : 0;
         const Ev e = eval_point<C::W, kEvRes>(w, agent, ent ? ent : C::W + 1, ko_key);
         const bool res = e.bad && ent != 0;
-        if (ent) elist[k] = (uint16_t)((uint32_t)ent | (res ? kResFlag : 0u));      // addReserve, :757-761
+        if (ent) est(elist + k, (uint32_t)ent | (res ? kResFlag : 0u));
         reserved_total += __popc(__ballot_sync(kFull, res));
     }
     __syncwarp();
@@ -271,19 +311,39 @@ AGB_NOINLINE int complex_pick(uint32_t* w, uint16_t* elist, int n_el, int spaces
     if (range != 0) {
         int rnd = (int)(draw % (uint32_t)range);
         *used = 1;
+        bool found = false;
+        // list order = the array from its end: first what is beyond the registers ...
 #pragma unroll 1
-        for (int top = n_el - 1; top >= 0; top -= 32) {
+        for (int top = n_el - 1; top >= 32 * kKeep && !found; top -= 32) {
             const int k = top - lane;                                               // lane order = list order
-            const uint32_t ent = k >= 0 ? (uint32_t)elist[k] : 0u;
+            const uint32_t ent = k >= 32 * kKeep ? eld(elist + k) : 0u;
             const bool ok = ent - 1u < 0x7fffu;                                     // alive and not reserved
             const unsigned m = __ballot_sync(kFull, ok);
             const int c = __popc(m);
             if (rnd < c) {
                 const bool hit = ok && __popc(m & ((1u << lane) - 1u)) == rnd;
                 pick = (int)__shfl_sync(kFull, ent, __ffs(__ballot_sync(kFull, hit)) - 1);
-                break;
+                found = true;
+            } else {
+                rnd -= c;
             }
-            rnd -= c;
+        }
+        // ... then the rounds in registers, last round first, high lane first
+#pragma unroll
+        for (int r = kKeep - 1; r >= 0; r--) {
+            if (!found && 32 * r < n_el) {
+                const bool ok = ents[r] - 1u < 0x7fffu;
+                const unsigned m = __ballot_sync(kFull, ok);
+                const int c = __popc(m);
+                if (rnd < c) {
+                    // the rnd-th from the top is the (c-1-rnd)-th from the bottom
+                    const bool hit = ok && __popc(m & ((1u << lane) - 1u)) == c - 1 - rnd;
+                    pick = (int)(__shfl_sync(kFull, ents[r], __ffs(__ballot_sync(kFull, hit)) - 1) & 0x1ffu);
+                    found = true;
+                } else {
+                    rnd -= c;
+                }
+            }
         }
     }
     return pick;
@@ -310,7 +370,7 @@ AGB_DEV int score_diff(const uint32_t* w, uint32_t agent, int lane) {
 
 // ---- the kernel body ----------------------------------------------------------------------------
 template <class C>
-AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int lane) {
+AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int lane, int warp_slot) {
     constexpr int G = C::G, W = C::W;
     constexpr uint32_t RM = (uint32_t)(C::R - 1);
     const int gl = lane & (G - 1);
@@ -319,7 +379,8 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
     uint32_t* const gsm = smem_warp + grp * C::words;
     uint16_t* const ring = reinterpret_cast<uint16_t*>(gsm + C::oRing);
     uint32_t* const w = gsm + C::oBoard;
-    uint16_t* const elist = reinterpret_cast<uint16_t*>(gsm + C::oElist);
+    uint16_t* const elist_warp = a.elist_scratch + (size_t)warp_slot * (C::NG * C::E);   // this warp's playouts
+    uint16_t* const elist = elist_warp + grp * C::E;
     uint16_t* const cbuf = reinterpret_cast<uint16_t*>(gsm + C::oCbuf);
     const uint4* __restrict__ jt = a.jump_bytes;
 
@@ -402,9 +463,9 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
 #pragma unroll 1
                 for (int i = lane; i < C::NP; i += 32) xw[i] = gp.w[i];          // Board::clone, Board.cpp:216-254
                 {
-                    uint32_t* xe = xsm + C::oElist;
+                    uint32_t* xe = reinterpret_cast<uint32_t*>(elist_warp + X * C::E);
 #pragma unroll 1
-                    for (int i = lane; i < (C::NN + 1) / 2; i += 32) xe[i] = gp.elist_w[i];
+                    for (int i = lane; i < (C::NN + 1) / 2; i += 32) est32(xe + i, gp.elist_w[i]);
                 }
                 __syncwarp();
                 int lm = gp.last[2 - d.first];                                   // last_move[enemy of the first mover]
@@ -584,7 +645,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     cm &= ~(C::GM << src);
                     uint32_t* const xsm = smem_warp + X * C::words;
                     uint32_t* const xw = xsm + C::oBoard;
-                    uint16_t* const xel = reinterpret_cast<uint16_t*>(xsm + C::oElist);
+                    uint16_t* const xel = elist_warp + X * C::E;
                     int xn = __shfl_sync(kFull, n_el, src);
                     int xd = __shfl_sync(kFull, n_dead, src);
                     const int xstones = __shfl_sync(kFull, stones, src);
@@ -617,7 +678,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 const bool maint = doput && n_dead >= 0;
                 if (__any_sync(kFull, maint)) {
                     if (maint) {
-                        if (gl == 0) elist[fNext(w[idx])] = 0;
+                        if (gl == 0) est(elist + fSlot(w[idx]), 0u);
                         n_dead++;
                     }
                     __syncwarp();
@@ -659,7 +720,8 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 t += __shfl_xor_sync(kFull, t, 2);
                 hp_total += t;
                 // the last stone of this lane's string: the root itself, or what its second stone says
-                const uint32_t nx = fNext(rw);
+                // (only an own stone has a next stone: on an empty point that field is its slot in elist)
+                const uint32_t nx = frnd ? fNext(rw) : kNilG;
                 const uint32_t sw = w[nx != kNilG ? nx : root];
                 const uint32_t tail = nx != kNilG ? fHp(sw) : root;
                 // lane of F_i links its tail to the head of F_(i-1), the lane of F_1 to the new stone
@@ -727,7 +789,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                         const int src = X * G;
                         full &= ~(C::GM << src);
                         uint32_t* const xsm = smem_warp + X * C::words;
-                        const int xn = compact<C>(xsm + C::oBoard, reinterpret_cast<uint16_t*>(xsm + C::oElist),
+                        const int xn = compact<C>(xsm + C::oBoard, elist_warp + X * C::E,
                                                   __shfl_sync(kFull, n_el, src), lane);
                         if (grp == X) { n_el = xn; if (n_dead > 0) n_dead = 0; }
                     }
@@ -741,7 +803,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                         if (act && fCol(vn) == colour) atomicAdd(&w[fA(vn)], kHpOne);
                         stones--;
                         if (gl == 0) {
-                            elist[n_el] = (uint16_t)kcur;                       // push at the list head, :311-321
+                            est(elist + n_el, kcur);                            // push at the list head, :311-321
                             w[kcur] = gw::empty(kcur, (uint32_t)n_el);          // empty, slot = n_el
                         }
                         n_el++;

@@ -25,7 +25,7 @@ struct Job {
 template <class C>
 void lane_entry(int lane, void* user) {
     Job<C>* j = (Job<C>*)user;
-    grp::playout_group_body<C>(j->a, j->smem, lane);
+    grp::playout_group_body<C>(j->a, j->smem, lane, 0);
 }
 
 template <class C>
@@ -36,6 +36,8 @@ void run(const KernelArgs& a) {
     uint32_t* smem = (uint32_t*)aligned_alloc(64, (((size_t)C::warp_words * 4 + 63) / 64) * 64);
     for (int i = 0; i < C::warp_words; i++) smem[i] = 0xdeadbeefu;
     j.smem = smem;
+    std::vector<uint16_t> scratch((size_t)C::NG * C::E, 0xdeadu);      // the warp's empty-point arrays (global memory)
+    j.a.elist_scratch = scratch.data();
     emu::run_warp(&lane_entry<C>, &j);
     free(smem);
 }

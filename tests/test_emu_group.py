@@ -66,3 +66,22 @@ def test_move_cap_is_a_fault():
     emu = emu_group()
     o, d, s, _ = emu_playouts(emu, 9, 8, [], 1, None, 8, max_moves=10)
     assert s[2] == 8 and (d == -32768).all() and o.sum() == 0
+
+
+def test_memory_bounds_under_address_sanitizer(tmp_path):
+    """The same source under -fsanitize=address, the warp's shared memory and its empty-point arrays
+    allocated exactly: an index that leaves them (on the GPU: into a neighbour's board, or past the
+    block's shared memory — an illegal address only when the block fills the SM) aborts the run."""
+    import subprocess
+    from util import ROOT
+    csrc = os.path.join(ROOT, "agentgo_b200", "csrc")
+    exe = str(tmp_path / "emu_asan")
+    srcs = [os.path.join(ROOT, "tests", "csrc", f) for f in ("emu_main.cpp", "emu_group.cpp", "simt_emu.cpp")] + \
+           [os.path.join(csrc, f) for f in ("host_board.cpp", "host_layout.cpp")]
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address", "-w", "-I", csrc, "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "tests", "csrc"), "-I", os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")]
+                          + srcs + ["-o", exe])
+    for n, lanes, P in ((19, 8, 10), (9, 8, 7), (19, 16, 4)):
+        r = subprocess.run([exe, str(n), str(lanes), str(P)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "ERROR" not in r.stderr, r.stderr[-1500:]
+        assert ("playouts %d" % P) in r.stdout
