@@ -209,6 +209,7 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     a.shard_count = shard_units ? cfg.shard_count : 1;
     const int64_t total = (int64_t)S * P;
     a.local_units = total > a.shard_rank ? (total - a.shard_rank + a.shard_count - 1) / a.shard_count : 0;
+    if (a.local_units >= (1ll << 32)) return fail(AGB_ERR_INVALID, "more than 2^32 playouts in one launch of one shard");
     a.work_counter = (unsigned long long*)d_small_;
     a.stats = (unsigned long long*)d_small_ + 1;
     a.counters = (long long*)d_counters_;

@@ -212,19 +212,34 @@ AGB_DEV uint4 jump_lookup(const uint4* __restrict__ tab, uint32_t g0, uint32_t g
 }
 template <class C>
 AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* __restrict__ jb, int gl) {
-    const uint4 t = jump_lookup(jb, st.g0, st.g1, st.g2, st.g3);       // matrix 0: T^BATCH
-    if (part) {         // (no collective inside: the lanes of a group that does not take part just wait)
-        TinyMT mine;
-        mine.s0 = st.g0; mine.s1 = st.g1; mine.s2 = st.g2; mine.s3 = st.g3;
-        uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
-#pragma unroll 2
-        for (int j = 0; j < C::SEG / 2; j++) {
-            mine.next_state(prm.mat1, prm.mat2);
-            const uint32_t lo = mine.temper(prm.tmat) >> 17;
-            mine.next_state(prm.mat1, prm.mat2);
-            const uint32_t hi = mine.temper(prm.tmat) >> 17;
-            out[j] = lo | (hi << 16);
+    static_assert(C::SEG % 8 == 0, "four quarters of an even number of draws");
+    TinyMT mine;
+    mine.s0 = st.g0; mine.s1 = st.g1; mine.s2 = st.g2; mine.s3 = st.g3;
+    uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
+    uint4 t = make_uint4(0, 0, 0, 0);
+    // four quarters: the lookups of a quarter of the state's bytes (matrix 0: T^BATCH) are issued, a
+    // quarter of the segment is generated while they are on their way from L2, then they are folded in
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const uint32_t word = q == 0 ? st.g0 : (q == 1 ? st.g1 : (q == 2 ? st.g2 : st.g3));
+        const uint4 u0 = __ldg(jb + (4 * q + 0) * 256 + (word & 255u));
+        const uint4 u1 = __ldg(jb + (4 * q + 1) * 256 + ((word >> 8) & 255u));
+        const uint4 u2 = __ldg(jb + (4 * q + 2) * 256 + ((word >> 16) & 255u));
+        const uint4 u3 = __ldg(jb + (4 * q + 3) * 256 + (word >> 24));
+        if (part) {     // (no collective inside: the lanes of a group that does not take part just wait)
+#pragma unroll
+            for (int j = 0; j < C::SEG / 8; j++) {
+                mine.next_state(prm.mat1, prm.mat2);
+                const uint32_t lo = mine.temper(prm.tmat) >> 17;
+                mine.next_state(prm.mat1, prm.mat2);
+                const uint32_t hi = mine.temper(prm.tmat) >> 17;
+                out[q * (C::SEG / 8) + j] = lo | (hi << 16);
+            }
         }
+        t.x ^= u0.x ^ u1.x ^ u2.x ^ u3.x; t.y ^= u0.y ^ u1.y ^ u2.y ^ u3.y;
+        t.z ^= u0.z ^ u1.z ^ u2.z ^ u3.z; t.w ^= u0.w ^ u1.w ^ u2.w ^ u3.w;
+    }
+    if (part) {
         st.g0 = t.x; st.g1 = t.y; st.g2 = t.z; st.g3 = t.w;
         st.gen_end += (uint32_t)C::BATCH;
     }
@@ -404,12 +419,12 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
     // state of this lane's playout, the same in all G lanes of the group
     enum { kFetch = 0, kPlay = 1, kEnded = 2, kDone = 3 };
     int phase = kFetch;
-    uint32_t colour = 1, first = 1;
+    uint32_t colour = 1;
+    bool closes = false;        // the move about to be made closes a pair (it is the second mover's)
     int prev = -1, stones = 0, ko_key = -1, ending = 0, n_el = 0, n_dead = -1;
     uint32_t pos = 0, mv = 0;
     GenState gs = {0, 0, 0, 0, 0};
-    int s_idx = 0;
-    long long gid = 0;
+    uint32_t unit = 0;          // which of this shard's units (the engine keeps a launch below 2^32 of them)
     bool fault = false;
 
 #pragma unroll 1
@@ -424,8 +439,9 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
             uint32_t* const xsm = smem_warp + X * C::words;
             uint32_t* const xw = xsm + C::oBoard;
             if (__shfl_sync(kFull, phase, src) == kEnded) {
-                const int xs = __shfl_sync(kFull, s_idx, src);
-                const long long xg = __shfl_sync(kFull, gid, src);
+                // (start and global id are worked out again from the unit: two registers less in the move loop)
+                const long long xg = (long long)__shfl_sync(kFull, unit, src) * a.shard_count + a.shard_rank;
+                const int xs = (int)(xg / a.P);
                 const uint32_t xmv = __shfl_sync(kFull, mv, src);
                 const uint32_t xpos = __shfl_sync(kFull, pos, src);
                 const bool xfault = __shfl_sync(kFull, (int)fault, src) != 0;
@@ -479,7 +495,8 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 if (gl != 0) { t.s0 = js.x; t.s1 = js.y; t.s2 = js.z; t.s3 = js.w; }
                 if (grp == X) {
                     phase = kPlay;
-                    colour = first = (uint32_t)d.first;
+                    colour = (uint32_t)d.first;
+                    closes = false;
                     prev = lm;
                     stones = gp.stones;
                     ko_key = gp.ko_key_col > 0 ? ((gp.ko_key_col << 16) | gp.ko_idx) : -1;
@@ -488,7 +505,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     n_dead = -1;
                     pos = 0; mv = 0;
                     gs.g0 = t.s0; gs.g1 = t.s1; gs.g2 = t.s2; gs.g3 = t.s3; gs.gen_end = 0;
-                    s_idx = s; gid = g; fault = false;
+                    unit = (uint32_t)l; fault = false;
                 }
             } else if (grp == X) {
                 phase = kDone;
@@ -821,11 +838,12 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
         if (live) {
             const int before = prev;
             prev = r;                                                           // Board.cpp:171 / :202
-            if (colour != first) {
+            if (closes) {
                 if ((before & r) < 0) phase = kEnded;
                 else if ((int)mv > a.max_moves) { fault = true; phase = kEnded; }   // fault detector, once per pair
             }
             colour = 3u - colour;
+            closes = !closes;
         }
 #undef AGB_ENSURE
     }
