@@ -159,14 +159,14 @@ def cpu_reference(cfg_id, sample_seconds, n_steps=1, warmup=0, threads=None):
         probe_P, what = 50, "all 81 candidates x %d playouts (candidate mode, 9x9 empty board)"
     elif cfg_id == 3:
         import agentgo_b200 as ag
-        pos = midgame_positions(ag, 32)
+        pos = midgame_positions(ag, 200)[::25]          # 8 positions spread over the batch's 40..239 moves
         boards = [po.OracleBoard(19, kind).replay(mv) for mv, _ in pos]
 
         def run(P, i):
             for k, ob in enumerate(boards):
-                ob.playouts(pos[k][1], None, P, seed_base=SEED_BASE + i, position_id=k, want_diffs=False, threads=threads)
+                ob.playouts(pos[k][1], None, P, seed_base=SEED_BASE + i, position_id=25 * k, want_diffs=False, threads=threads)
             return len(boards) * P
-        probe_P, what = 100, "the first 32 positions of the batch x %d root-mode playouts"
+        probe_P, what = 1000, "positions 0, 25, ..., 175 of the batch x %d root-mode playouts each"
     else:
         b = po.OracleBoard(19, kind)
 
@@ -505,15 +505,14 @@ def run_selfplay(args):
         sys.stderr.write(out.stderr[-2000:])
         return out.returncode
     sp = json.loads(out.stdout.strip().splitlines()[-1])["selfplay"]
-    value = sp["playouts"] / (sp["genmoves"] * sp["device_ms_median"] * 1e-3) if sp["genmoves"] else 0.0
-    line = {"metric": metric_name(4), "value": sp["playouts"] / max(1e-9, sum([sp["device_ms_median"]]) * sp["genmoves"] * 1e-3),
-            "unit": UNIT, "n_gpus": args.gpus, "steps": sp["genmoves"], "warmup": 0,
+    # playouts per second of device time, from the median genmove (the engine reports the median, not the sum)
+    value = sp["playouts"] / max(1e-9, sp["genmoves"] * sp["device_ms_median"] * 1e-3)
+    line = {"metric": metric_name(4), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": sp["genmoves"], "warmup": 0,
             "ms_per_step": sp["device_ms_median"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32", "data": "synthetic", "config": workload(4, args.playouts, args.gpus),
             "e2e": {"value": sp["playouts"] / wall, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
                     "note": "whole process wall clock incl. start-up"},
             "genmove": sp, "impl": "b200", "command": " ".join(cmd[1:])}
-    del value
     print(json.dumps(line))
     return 0
 
