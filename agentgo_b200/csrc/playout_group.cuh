@@ -97,7 +97,11 @@ struct GCfg {
     static constexpr int E = kGroupElistCap;        // elist entries, in global memory (kernel_args.h)
     // shared-memory words of one playout: ring | board | cbuf, a multiple of 4
     static constexpr int oRing = 0, oBoard = R / 2, oCbuf = oBoard + NP;
-    static constexpr int words = ((oCbuf + G / 2 + 3) / 4) * 4;    // cbuf: G 16-bit entries, the candidates of a move
+    // cbuf: G 16-bit entries, the candidates of a move.  The stride from one playout of a warp to the next
+    // is a multiple of 4 words (the ring is written with 128-bit stores) and = 8 mod 32, so that the
+    // same field of the four playouts of a warp (cbuf, ring position, board word) sits in different banks.
+    static constexpr int words4 = ((oCbuf + G / 2 + 3) / 4) * 4;
+    static constexpr int words = words4 + ((8 - words4 % 32) + 32) % 32;
     static constexpr int warp_words = NG * words;
     static constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
 };
