@@ -11,6 +11,13 @@ namespace agb {
 
 static const size_t kSmallWords = 8;   // [0] work counter, [1..4] stats
 
+// MyGame::testAvrgWin's result, AgentGo.cpp:447: int(sum of the root playouts' scores / their number),
+// C truncation, from the (all-reduced) root counters — on the device, so that the candidate launch can
+// follow the root launch without a host round trip
+__global__ void avrg_win_kernel(const long long* counters, int stride, long long playouts, int* out) {
+    out[0] = (int)((counters[stride] + counters[2 * stride]) / playouts);
+}
+
 int Engine::cuda_fail(cudaError_t e, const char* what) {
     char buf[256];
     snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
@@ -77,8 +84,11 @@ int Engine::create(const agb_config& cfg, Engine** out, std::string* err) {
     if ((e = cudaSetDevice(cfg.device)) != cudaSuccess ||
         (e = cudaGetDeviceProperties(&prop, cfg.device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&h->stream_, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaEventCreate(&h->ev0_)) != cudaSuccess || (e = cudaEventCreate(&h->ev1_)) != cudaSuccess ||
-        (e = cudaMalloc(&h->d_small_, kSmallWords * sizeof(unsigned long long))) != cudaSuccess) {
+        (e = cudaEventCreate(&h->slot_[0].ev0)) != cudaSuccess || (e = cudaEventCreate(&h->slot_[0].ev1)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->slot_[1].ev0)) != cudaSuccess || (e = cudaEventCreate(&h->slot_[1].ev1)) != cudaSuccess ||
+        (e = cudaMalloc(&h->slot_[0].d_small, kSmallWords * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&h->slot_[1].d_small, kSmallWords * sizeof(unsigned long long))) != cudaSuccess ||
+        (e = cudaMalloc(&h->d_avrg_, sizeof(int))) != cudaSuccess) {
         if (err) *err = std::string("CUDA init: ") + cudaGetErrorString(e);
         delete h;
         return AGB_ERR_CUDA;
@@ -105,12 +115,15 @@ Engine::~Engine() {
     if (cfg.device < 0) return;
     cudaSetDevice(cfg.device);
     if (stream_) cudaStreamSynchronize(stream_);
-    cudaFree(d_starts_); cudaFree(d_descs_); cudaFree(d_counters_); cudaFree(d_diffs_);
-    cudaFree(d_gather_); cudaFree(d_elist_); cudaFree(d_small_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_amaf_);
-    if (h_pinned_) cudaFreeHost(h_pinned_);
-    if (h_stage_) cudaFreeHost(h_stage_);
-    if (ev0_) cudaEventDestroy(ev0_);
-    if (ev1_) cudaEventDestroy(ev1_);
+    for (Slot& t : slot_) {
+        cudaFree(t.d_starts); cudaFree(t.d_descs); cudaFree(t.d_counters); cudaFree(t.d_small);
+        if (t.h_pinned) cudaFreeHost(t.h_pinned);
+        if (t.h_stage) cudaFreeHost(t.h_stage);
+        if (t.ev0) cudaEventDestroy(t.ev0);
+        if (t.ev1) cudaEventDestroy(t.ev1);
+    }
+    cudaFree(d_diffs_); cudaFree(d_gather_); cudaFree(d_elist_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_amaf_);
+    cudaFree(d_avrg_);
     if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -128,7 +141,7 @@ int Engine::ensure(void** ptr, size_t* cap, size_t bytes) {
 int Engine::launch(const std::vector<Position>& starts, const std::vector<StartDesc>& descs, int64_t P,
                    uint64_t seed_base, bool want_diffs, bool shard_units, bool want_amaf, int counter_stride) {
     if (cfg.device < 0) return fail(AGB_ERR_CUDA, "engine was created without a CUDA device (device = -1); no CPU fallback");
-    if (in_flight_) return fail(AGB_ERR_STATE, "a launch is already in flight");
+    if (sl().in_flight) return fail(AGB_ERR_STATE, "a launch is already in flight");
     if (starts.empty() || starts.size() != descs.size() || P <= 0)
         return fail(AGB_ERR_INVALID, "nothing to launch");
     AGB_CUDA(cudaSetDevice(cfg.device));
@@ -138,11 +151,20 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     const bool thread_kernel = cfg.kernel == AGB_KERNEL_THREAD;
     if (want_amaf && thread_kernel)
         return fail(AGB_ERR_INVALID, "AMAF marks are implemented by the warp kernel only");
-    // lanes per playout of the group kernel, 0 = another kernel.  AMAF marks are recorded by the
-    // warp kernel.
+    // this shard's share of the launch
+    const int sh_rank = shard_units ? cfg.shard_rank : 0, sh_count = shard_units ? cfg.shard_count : 1;
+    const int64_t total = (int64_t)S * P;
+    const int64_t local_units = total > sh_rank ? (total - sh_rank + sh_count - 1) / sh_count : 0;
+    // Lanes per playout of the group kernel, 0 = another kernel.  AMAF marks are recorded by the warp
+    // kernel.  AGB_KERNEL_AUTO: the group kernel (four playouts per warp) has the higher THROUGHPUT
+    // (+9 % at 19x19), the warp kernel the lower LATENCY per playout (a warp serves one playout, not
+    // four in lock step), so a launch of less than about two loads of the machine (100 playouts per SM)
+    // finishes earlier on the warp kernel: 0.8 ms against 2.6 ms for 2 000 playouts at 19x19, equal at
+    // 32 000 (tests/latency_probe.py).  The reference's own genmove is 25 850 playouts.
     int group_lanes = 0;
     if (!want_amaf) {
-        if (cfg.kernel == AGB_KERNEL_GROUP8 || cfg.kernel == AGB_KERNEL_AUTO) group_lanes = 8;
+        if (cfg.kernel == AGB_KERNEL_GROUP8) group_lanes = 8;
+        else if (cfg.kernel == AGB_KERNEL_AUTO) group_lanes = local_units >= 2 * (int64_t)sm_count_ * 100 ? 8 : 0;
         else if (cfg.kernel == AGB_KERNEL_GROUP16) group_lanes = 16;
         else if (cfg.kernel == AGB_KERNEL_GROUP32) group_lanes = 32;
     }
@@ -152,39 +174,39 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
         AGB_CUDA(cudaMemsetAsync(d_amaf_, 0, amaf_bytes, stream_));
     }
     const size_t start_bytes = (thread_kernel ? sizeof(Position) : (group_lanes ? sizeof(GroupPosition) : sizeof(PaddedPosition))) * (size_t)S;
-    if ((st = ensure(&d_starts_, &cap_starts_, start_bytes))) return st;
-    if ((st = ensure(&d_descs_, &cap_descs_, sizeof(StartDesc) * (size_t)S))) return st;
-    if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)stride))) return st;
+    if ((st = ensure(&sl().d_starts, &sl().cap_starts, start_bytes))) return st;
+    if ((st = ensure(&sl().d_descs, &sl().cap_descs, sizeof(StartDesc) * (size_t)S))) return st;
+    if ((st = ensure(&sl().d_counters, &sl().cap_counters, sizeof(long long) * 3 * (size_t)stride))) return st;
     if (want_diffs && (st = ensure(&d_diffs_, &cap_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P))) return st;
 
     // inputs are staged in PINNED host memory and copied asynchronously on the engine's stream
     const size_t desc_bytes = sizeof(StartDesc) * (size_t)S;
-    if (cap_stage_ < start_bytes + desc_bytes) {
-        if (h_stage_) cudaFreeHost(h_stage_);
-        h_stage_ = nullptr; cap_stage_ = 0;
-        AGB_CUDA(cudaMallocHost(&h_stage_, start_bytes + desc_bytes));
-        cap_stage_ = start_bytes + desc_bytes;
+    if (sl().cap_stage < start_bytes + desc_bytes) {
+        if (sl().h_stage) cudaFreeHost(sl().h_stage);
+        sl().h_stage = nullptr; sl().cap_stage = 0;
+        AGB_CUDA(cudaMallocHost(&sl().h_stage, start_bytes + desc_bytes));
+        sl().cap_stage = start_bytes + desc_bytes;
     }
     if (thread_kernel) {
-        memcpy(h_stage_, starts.data(), start_bytes);
+        memcpy(sl().h_stage, starts.data(), start_bytes);
     } else if (group_lanes) {
-        GroupPosition* gp = (GroupPosition*)h_stage_;
+        GroupPosition* gp = (GroupPosition*)sl().h_stage;
         for (int i = 0; i < S; i++) to_group(starts[i], &gp[i]);
     } else {
-        PaddedPosition* pp = (PaddedPosition*)h_stage_;
+        PaddedPosition* pp = (PaddedPosition*)sl().h_stage;
         for (int i = 0; i < S; i++) to_padded(starts[i], &pp[i]);
     }
-    memcpy((char*)h_stage_ + start_bytes, descs.data(), desc_bytes);
-    AGB_CUDA(cudaMemcpyAsync(d_starts_, h_stage_, start_bytes, cudaMemcpyHostToDevice, stream_));
-    AGB_CUDA(cudaMemcpyAsync(d_descs_, (char*)h_stage_ + start_bytes, desc_bytes, cudaMemcpyHostToDevice, stream_));
-    AGB_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(long long) * 3 * (size_t)stride, stream_));
-    AGB_CUDA(cudaMemsetAsync(d_small_, 0, kSmallWords * sizeof(unsigned long long), stream_));
+    memcpy((char*)sl().h_stage + start_bytes, descs.data(), desc_bytes);
+    AGB_CUDA(cudaMemcpyAsync(sl().d_starts, sl().h_stage, start_bytes, cudaMemcpyHostToDevice, stream_));
+    AGB_CUDA(cudaMemcpyAsync(sl().d_descs, (char*)sl().h_stage + start_bytes, desc_bytes, cudaMemcpyHostToDevice, stream_));
+    AGB_CUDA(cudaMemsetAsync(sl().d_counters, 0, sizeof(long long) * 3 * (size_t)stride, stream_));
+    AGB_CUDA(cudaMemsetAsync(sl().d_small, 0, kSmallWords * sizeof(unsigned long long), stream_));
 
     KernelArgs a;
     memset(&a, 0, sizeof(a));
-    a.starts = (const Position*)d_starts_;
-    a.pstarts = (const PaddedPosition*)d_starts_;
-    a.gstarts = (const GroupPosition*)d_starts_;
+    a.starts = (const Position*)sl().d_starts;
+    a.pstarts = (const PaddedPosition*)sl().d_starts;
+    a.gstarts = (const GroupPosition*)sl().d_starts;
     a.jump = (const JumpTable*)d_jump_;
     if (group_lanes) {
         // the per-lane jump matrices of the group kernel, built on first use for this lane count
@@ -201,25 +223,25 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
         if ((st = ensure(&d_elist_, &cap_elist_, (size_t)sm_count_ * kGroupMaxPlayoutsPerSm * kGroupElistCap * sizeof(uint16_t)))) return st;
         a.elist_scratch = (uint16_t*)d_elist_;
     }
-    a.descs = (const StartDesc*)d_descs_;
+    a.descs = (const StartDesc*)sl().d_descs;
     a.n_starts = S;
     a.P = P;
     a.seed_base = seed_base;
-    a.shard_rank = shard_units ? cfg.shard_rank : 0;
-    a.shard_count = shard_units ? cfg.shard_count : 1;
-    const int64_t total = (int64_t)S * P;
-    a.local_units = total > a.shard_rank ? (total - a.shard_rank + a.shard_count - 1) / a.shard_count : 0;
+    a.shard_rank = sh_rank;
+    a.shard_count = sh_count;
+    a.local_units = local_units;
     if (a.local_units >= (1ll << 32)) return fail(AGB_ERR_INVALID, "more than 2^32 playouts in one launch of one shard");
-    a.work_counter = (unsigned long long*)d_small_;
-    a.stats = (unsigned long long*)d_small_ + 1;
-    a.counters = (long long*)d_counters_;
+    a.work_counter = (unsigned long long*)sl().d_small;
+    a.stats = (unsigned long long*)sl().d_small + 1;
+    a.counters = (long long*)sl().d_counters;
     a.counter_stride = stride;
     a.diffs = want_diffs ? (int16_t*)d_diffs_ : nullptr;
     a.amaf = want_amaf ? (long long*)d_amaf_ : nullptr;
     a.rng.mat1 = cfg.mat1; a.rng.mat2 = cfg.mat2; a.rng.tmat = cfg.tmat;
     a.max_moves = cfg.max_moves;
+    a.avrg_dev = avrg_from_device_ ? d_avrg_ : nullptr;
 
-    AGB_CUDA(cudaEventRecord(ev0_, stream_));
+    AGB_CUDA(cudaEventRecord(sl().ev0, stream_));
     if (a.local_units > 0) {
         cudaError_t e;
         const int n = board.n();
@@ -228,20 +250,20 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
         else e = launch_playout_warp(n, a, sm_count_, stream_, &info_);
         if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
     }
-    in_flight_ = true;
-    n_starts_ = S; stride_ = stride; P_ = P; want_diffs_ = want_diffs; shard_units_ = shard_units; want_amaf_ = want_amaf;
+    sl().in_flight = true;
+    sl().n_starts = S; sl().stride = stride; sl().P = P; sl().want_diffs = want_diffs; sl().shard_units = shard_units; sl().want_amaf = want_amaf;
     return AGB_OK;
 }
 
 int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* diffs, agb_stats* stats,
                    int64_t* amaf) {
-    if (!in_flight_) return fail(AGB_ERR_STATE, "no launch in flight");
+    if (!sl().in_flight) return fail(AGB_ERR_STATE, "no launch in flight");
     // everything that can be refused is refused before anything is enqueued behind the kernel
-    if (amaf && !want_amaf_) return fail(AGB_ERR_STATE, "the launch in flight did not record AMAF marks");
-    in_flight_ = false;
+    if (amaf && !sl().want_amaf) return fail(AGB_ERR_STATE, "the launch in flight did not record AMAF marks");
+    sl().in_flight = false;
     AGB_CUDA(cudaSetDevice(cfg.device));
-    const int S = n_starts_;
-    const int T = stride_;      // the counter table is [3][T], T >= S
+    const int S = sl().n_starts;
+    const int T = sl().stride;      // the counter table is [3][T], T >= S
     // an error from here on leaves work queued on the stream that may still write the caller's
     // buffers: wait for it before returning
     auto bail = [&](int status, const char* msg) {
@@ -250,36 +272,36 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
     };
     // snapshot the shard-local stats before any collective touches the counters
     const size_t need = sizeof(long long) * 3 * (size_t)T + kSmallWords * sizeof(unsigned long long);
-    if (cap_pinned_ < need) {
-        if (h_pinned_) cudaFreeHost(h_pinned_);
-        h_pinned_ = nullptr; cap_pinned_ = 0;
-        if (cudaMallocHost(&h_pinned_, need) != cudaSuccess) return bail(AGB_ERR_NOMEM, "cudaMallocHost failed");
-        cap_pinned_ = need;
+    if (sl().cap_pinned < need) {
+        if (sl().h_pinned) cudaFreeHost(sl().h_pinned);
+        sl().h_pinned = nullptr; sl().cap_pinned = 0;
+        if (cudaMallocHost(&sl().h_pinned, need) != cudaSuccess) return bail(AGB_ERR_NOMEM, "cudaMallocHost failed");
+        sl().cap_pinned = need;
     }
     if (allreduce_) {
-        int r = allreduce_(allreduce_ctx_, d_counters_, 3 * T, (void*)stream_);
+        int r = allreduce_(allreduce_ctx_, sl().d_counters, 3 * T, (void*)stream_);
         if (r) return bail(AGB_ERR_CUDA, "allreduce callback failed");
-        if (want_amaf_) {
+        if (sl().want_amaf) {
             r = allreduce_(allreduce_ctx_, d_amaf_, AGB_AMAF_WORDS(board.n()) * amaf_classes(), (void*)stream_);
             if (r) return bail(AGB_ERR_CUDA, "allreduce callback failed");
         }
     }
     // device time of the evaluation = kernel (+ collective), stream ordered
-    AGB_CUDA(cudaEventRecord(ev1_, stream_));
-    long long* hc = (long long*)h_pinned_;
+    AGB_CUDA(cudaEventRecord(sl().ev1, stream_));
+    long long* hc = (long long*)sl().h_pinned;
     unsigned long long* hs = (unsigned long long*)(hc + 3 * (size_t)T);
-    AGB_CUDA(cudaMemcpyAsync(hc, d_counters_, sizeof(long long) * 3 * (size_t)T, cudaMemcpyDeviceToHost, stream_));
-    AGB_CUDA(cudaMemcpyAsync(hs, d_small_, kSmallWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
-    if (diffs && want_diffs_ && !(shard_units_ && cfg.shard_count > 1))
-        AGB_CUDA(cudaMemcpyAsync(diffs, d_diffs_, sizeof(int16_t) * (size_t)S * (size_t)P_, cudaMemcpyDeviceToHost, stream_));
+    AGB_CUDA(cudaMemcpyAsync(hc, sl().d_counters, sizeof(long long) * 3 * (size_t)T, cudaMemcpyDeviceToHost, stream_));
+    AGB_CUDA(cudaMemcpyAsync(hs, sl().d_small, kSmallWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_));
+    if (diffs && sl().want_diffs && !(sl().shard_units && cfg.shard_count > 1))
+        AGB_CUDA(cudaMemcpyAsync(diffs, d_diffs_, sizeof(int16_t) * (size_t)S * (size_t)sl().P, cudaMemcpyDeviceToHost, stream_));
     if (amaf) {
         AGB_CUDA(cudaMemcpyAsync(amaf, d_amaf_, sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n()) * (size_t)amaf_classes(),
                                  cudaMemcpyDeviceToHost, stream_));
     }
     AGB_CUDA(cudaStreamSynchronize(stream_));
-    if (diffs && want_diffs_ && shard_units_ && cfg.shard_count > 1) {
+    if (diffs && sl().want_diffs && sl().shard_units && cfg.shard_count > 1) {
         // only this shard's entries are defined on the device; leave the others untouched
-        std::vector<int16_t> tmp((size_t)S * (size_t)P_);
+        std::vector<int16_t> tmp((size_t)S * (size_t)sl().P);
         AGB_CUDA(cudaMemcpy(tmp.data(), d_diffs_, sizeof(int16_t) * tmp.size(), cudaMemcpyDeviceToHost));
         for (int64_t g = cfg.shard_rank; g < (int64_t)tmp.size(); g += cfg.shard_count) diffs[g] = tmp[g];
     }
@@ -289,7 +311,7 @@ int Engine::finish(int64_t* wins, int64_t* sum_pos, int64_t* sum_neg, int16_t* d
         if (sum_neg) sum_neg[s] = hc[2 * T + s];
     }
     float ms = 0.f;
-    AGB_CUDA(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    AGB_CUDA(cudaEventElapsedTime(&ms, sl().ev0, sl().ev1));
     const unsigned long long* stv = hs + 1;
     if (stats) {
         stats->device_ms = ms;
@@ -388,14 +410,14 @@ int Engine::playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t s
     } else if (gather) {
         // nothing to play here, but the collective needs this shard's (empty) table
         AGB_CUDA(cudaSetDevice(cfg.device));
-        if ((st = ensure(&d_counters_, &cap_counters_, sizeof(long long) * 3 * (size_t)stride))) return st;
-        AGB_CUDA(cudaMemsetAsync(d_counters_, 0, sizeof(long long) * 3 * (size_t)stride, stream_));
+        if ((st = ensure(&sl().d_counters, &sl().cap_counters, sizeof(long long) * 3 * (size_t)stride))) return st;
+        AGB_CUDA(cudaMemsetAsync(sl().d_counters, 0, sizeof(long long) * 3 * (size_t)stride, stream_));
     }
     std::vector<long long> table;
     if (gather) {
         const size_t words = (size_t)R * 3 * (size_t)stride;
         if ((st = ensure(&d_gather_, &cap_gather_, sizeof(long long) * words))) return st;
-        if (allgather_(allgather_ctx_, d_counters_, d_gather_, 3 * stride, (void*)stream_))
+        if (allgather_(allgather_ctx_, sl().d_counters, d_gather_, 3 * stride, (void*)stream_))
             return fail(AGB_ERR_CUDA, "allgather callback failed");
         table.resize(words);
         AGB_CUDA(cudaMemcpyAsync(table.data(), d_gather_, sizeof(long long) * words, cudaMemcpyDeviceToHost, stream_));
@@ -457,17 +479,46 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
         if (stats) *stats = acc;
         return AGB_OK;
     }
-    int64_t w = 0, sp = 0, sn = 0;
-    int st = playouts_launch(colour, nullptr, 0, P_root, 0, seed_base, 0, false);
-    if (st) return st;
-    if ((st = finish(&w, &sp, &sn, nullptr, &st1))) return st;
-    acc = st1;
-    const int avrg_win = (int)((sp + sn) / P_root);          // C truncation, AgentGo.cpp:447
+    // The candidates do not depend on the root playouts (:586-592), only their threshold avrg_win does
+    // (:579).  So both launches go out back to back on the engine's stream — root playouts (slot 1),
+    // their allreduce, avrg_win worked out ON THE DEVICE, candidate playouts reading it from there
+    // (slot 0) — and the host waits once, at the end.
     std::vector<int16_t> cand;
     for (int i = 0; i < n; i++)
         for (int j = 0; j < n; j++)
             if (board.is_candidate(colour, i, j)) { cand.push_back((int16_t)i); cand.push_back((int16_t)j); }
     const int C = (int)cand.size() / 2;
+    int st;
+    cur_ = 1;
+    st = playouts_launch(colour, nullptr, 0, P_root, 0, seed_base, 0, false);
+    cur_ = 0;
+    if (st) return st;
+    Slot& root = slot_[1];
+    auto drop_root = [&](int status) {      // an error after the root launch: wait for it, forget it
+        cudaStreamSynchronize(stream_);
+        root.in_flight = false;
+        avrg_from_device_ = false;
+        return status;
+    };
+    if (allreduce_ && allreduce_(allreduce_ctx_, root.d_counters, 3 * root.stride, (void*)stream_))
+        return drop_root(fail(AGB_ERR_CUDA, "allreduce callback failed"));
+    avrg_win_kernel<<<1, 1, 0, stream_>>>((const long long*)root.d_counters, root.stride, (long long)P_root, d_avrg_);
+    // root results for the host: counters, statistics, avrg_win (pinned; complete at the final wait)
+    const size_t root_need = sizeof(long long) * 3 + kSmallWords * sizeof(unsigned long long) + sizeof(long long);
+    if (root.cap_pinned < root_need) {
+        if (root.h_pinned) cudaFreeHost(root.h_pinned);
+        root.h_pinned = nullptr; root.cap_pinned = 0;
+        if (cudaMallocHost(&root.h_pinned, root_need) != cudaSuccess) return drop_root(fail(AGB_ERR_NOMEM, "cudaMallocHost failed"));
+        root.cap_pinned = root_need;
+    }
+    long long* rc_h = (long long*)root.h_pinned;
+    unsigned long long* rs_h = (unsigned long long*)(rc_h + 3);
+    int* avrg_h = (int*)(rs_h + kSmallWords);
+    if (cudaMemcpyAsync(rc_h, root.d_counters, sizeof(long long) * 3, cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+        cudaMemcpyAsync(rs_h, root.d_small, kSmallWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream_) != cudaSuccess ||
+        cudaMemcpyAsync(avrg_h, d_avrg_, sizeof(int), cudaMemcpyDeviceToHost, stream_) != cudaSuccess)
+        return drop_root(fail(AGB_ERR_CUDA, "cudaMemcpyAsync failed"));
+    AGB_CUDA(cudaEventRecord(root.ev1, stream_));
     *is_pass = 1; *row = -1; *col = -1;
     {
         // (no candidate survives the filter: nothing is played out, but the reference still takes the
@@ -478,13 +529,30 @@ int Engine::genmove(int colour, int64_t P_cand, int64_t P_root, uint64_t seed_ba
         const bool use_amaf = C > 0 && cfg.genmove_amaf != 0 && cfg.kernel != AGB_KERNEL_THREAD;
         std::vector<int64_t> amaf;
         if (C > 0) {
-            st = playouts_launch(colour, cand.data(), C, P_cand, avrg_win, seed_base + 1, 0, false, use_amaf, use_amaf);
-            if (st) return st;
+            avrg_from_device_ = true;       // the kernel takes avrg_win from d_avrg_, not from the descriptors
+            st = playouts_launch(colour, cand.data(), C, P_cand, 0, seed_base + 1, 0, false, use_amaf, use_amaf);
+            avrg_from_device_ = false;
+            if (st) return drop_root(st);
             if (use_amaf) amaf.resize((size_t)AGB_AMAF_WORDS(n) * (size_t)amaf_classes());
-            if ((st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1, use_amaf ? amaf.data() : nullptr))) return st;
-            acc.device_ms += st1.device_ms; acc.playouts += st1.playouts; acc.moves += st1.moves;
-            acc.rng_draws += st1.rng_draws; acc.kernel_launches += st1.kernel_launches;
+            st = finish(cw.data(), csp.data(), csn.data(), nullptr, &st1, use_amaf ? amaf.data() : nullptr);   // waits for the stream
+            if (st) return drop_root(st);
+        } else {
+            AGB_CUDA(cudaStreamSynchronize(stream_));
+            memset(&st1, 0, sizeof(st1));
         }
+        root.in_flight = false;
+        // both launches are complete: the root's results are in pinned memory
+        const unsigned long long* rst = rs_h + 1;
+        if (rst[kStatFaults] != 0) return fail(AGB_ERR_FAULT, "a playout exceeded the move cap");
+        const int avrg_win = *avrg_h;                             // int((sp + sn) / P_root), AgentGo.cpp:447
+        float ms = 0.f;
+        AGB_CUDA(cudaEventElapsedTime(&ms, root.ev0, C > 0 ? slot_[0].ev1 : root.ev1));
+        acc.device_ms = ms;                                       // root launch to the end of the candidates' collective
+        acc.playouts = (int64_t)rst[kStatPlayouts] + st1.playouts;
+        acc.moves = (int64_t)rst[kStatMoves] + st1.moves;
+        acc.rng_draws = (int64_t)rst[kStatDraws] + st1.rng_draws;
+        acc.kernel_launches = 1 + st1.kernel_launches;
+        last_avrg_win = avrg_win;
         const double index_c = cfg.index_c;
         const double cnsv = std::pow(2.0, avrg_win * cfg.index_cnsv);    // AgentGo.cpp:25,99
         // AMAF terms (:86-94,:329-338): decay table over the step of the first play.  The table

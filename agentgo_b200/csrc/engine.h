@@ -53,14 +53,15 @@ public:
                 int* is_pass, agb_stats* stats);
 
     int genmove_step = 0;                // MyGame::step, AgentGo.cpp:353
+    int last_avrg_win = 0;               // avrg_win of the last genmove (testAvrgWin)
     std::vector<double> last_marks;      // total_mark of the last genmove (empty after a book move)
 
-    void* counters_dev() const { return d_counters_; }
+    void* counters_dev() const { return slot_[0].d_counters; }
     cudaStream_t stream() const { return stream_; }
     void set_allreduce(AllreduceFn fn, void* ctx) { allreduce_ = fn; allreduce_ctx_ = ctx; }
     void set_allgather(AllgatherFn fn, void* ctx) { allgather_ = fn; allgather_ctx_ = ctx; }
     int fail(int status, const std::string& msg) { err = msg; return status; }
-    bool busy() const { return in_flight_; }     // between *_launch and *_finish: the position must not change
+    bool busy() const { return slot_[0].in_flight || slot_[1].in_flight; }   // between *_launch and *_finish: the position must not change
 
 private:
     Engine() : board(13) {}
@@ -69,27 +70,34 @@ private:
 
     int sm_count_ = 0;
     cudaStream_t stream_ = nullptr;
-    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
-    void* d_starts_ = nullptr; size_t cap_starts_ = 0;
+    // Buffers and state of one launch.  Two slots: genmove keeps the root launch (testAvrgWin) and the
+    // candidate launch in flight together, stream-ordered, so that no host round trip separates them.
+    struct Slot {
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        void* d_starts = nullptr; size_t cap_starts = 0;
+        void* h_stage = nullptr; size_t cap_stage = 0;   // pinned staging of the start positions + descriptors
+        void* d_descs = nullptr; size_t cap_descs = 0;
+        void* d_counters = nullptr; size_t cap_counters = 0;
+        void* d_small = nullptr;            // work counter + stats
+        void* h_pinned = nullptr; size_t cap_pinned = 0;
+        // state of the launch in flight
+        bool in_flight = false;
+        int n_starts = 0;
+        int stride = 0;                     // counter stride of the launch in flight
+        int64_t P = 0;
+        bool want_diffs = false, shard_units = false, want_amaf = false;
+    };
+    Slot slot_[2];
+    int cur_ = 0;
+    Slot& sl() { return slot_[cur_]; }
     void* d_jump_ = nullptr;             // JumpTable (TinyMT32 T^16), built at create time
     void* d_jump_bytes_ = nullptr; size_t cap_jump_bytes_ = 0;   // JumpBytes of the group kernel
     void* d_elist_ = nullptr; size_t cap_elist_ = 0;   // group kernel: empty-point arrays of the resident playouts
     int jump_bytes_lanes_ = 0;           // lanes per playout d_jump_bytes_ was built for
-    void* h_stage_ = nullptr; size_t cap_stage_ = 0;   // pinned staging of the start positions + descriptors
-    void* d_descs_ = nullptr; size_t cap_descs_ = 0;
-    void* d_counters_ = nullptr; size_t cap_counters_ = 0;
     void* d_diffs_ = nullptr; size_t cap_diffs_ = 0;
-    void* d_small_ = nullptr;            // work counter + stats
     void* d_amaf_ = nullptr; size_t cap_amaf_ = 0;   // AMAF table [2][2][41][NN] int64
-    void* h_pinned_ = nullptr; size_t cap_pinned_ = 0;
-
-    // state of the launch in flight
-    bool in_flight_ = false;
-    int n_starts_ = 0;
-    int64_t P_ = 0;
-    bool want_diffs_ = false;
-    bool shard_units_ = false;
-    bool want_amaf_ = false;
+    int* d_avrg_ = nullptr;              // avrg_win of the genmove in flight, computed on the device
+    bool avrg_from_device_ = false;      // the next launch reads avrg_win from d_avrg_
     std::vector<int> amaf_class_stones_ = std::vector<int>(1, 0);
     LaunchInfo info_ = {0, 0, 0, ""};
     AllreduceFn allreduce_ = nullptr;
@@ -97,7 +105,6 @@ private:
     AllgatherFn allgather_ = nullptr;    // batch path: gathers every shard's [3][stride] table
     void* allgather_ctx_ = nullptr;
     void* d_gather_ = nullptr; size_t cap_gather_ = 0;
-    int stride_ = 0;                     // counter stride of the launch in flight
 };
 
 }  // namespace agb

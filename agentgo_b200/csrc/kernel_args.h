@@ -114,6 +114,8 @@ struct KernelArgs {
     unsigned long long* stats;  // device [4]: moves, rng draws, faults, playouts
     RngParams rng;
     int32_t max_moves;
+    const int* avrg_dev;        // device, or nullptr: when set, avrg_win of every start is read from here (genmove:
+                                // the root playouts that determine it are still in flight when this launch is built)
 };
 
 enum StatSlot { kStatMoves = 0, kStatDraws = 1, kStatFaults = 2, kStatPlayouts = 3, kStatCount = 4 };

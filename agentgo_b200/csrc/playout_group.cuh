@@ -458,7 +458,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     if (xfault) atomicAdd(&a.stats[kStatFaults], 1ull);
                     if (a.diffs) a.diffs[xg] = (int16_t)diff;
                     if (!xfault) {
-                        const int wr = diff - d.avrg_win;                        // AgentGo.cpp:327
+                        const int wr = diff - (a.avrg_dev ? *a.avrg_dev : d.avrg_win);       // AgentGo.cpp:327
                         unsigned long long* c = (unsigned long long*)a.counters;
                         if (wr >= 0) {                                           // sign test of AgentGo.cpp:328
                             atomicAdd(&c[xs], 1ull);

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) playout_thread_kernel(const Ker
         if (diff == -32768) {
             faults++;
         } else {
-            const int w = diff - d.avrg_win;                 // AgentGo.cpp:327
+            const int w = diff - (a.avrg_dev ? __ldg(a.avrg_dev) : d.avrg_win);       // AgentGo.cpp:327
             unsigned long long* c = (unsigned long long*)a.counters;
             if (w >= 0) {                                    // sign test of AgentGo.cpp:328
                 atomicAdd(&c[s], 1ull);

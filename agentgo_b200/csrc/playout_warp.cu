@@ -875,7 +875,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             // :329-338 — point q counts for the agent table when the agent's first play there has
             // cstep <= 40, else for the enemy table when the enemy's has (the `else if`)
             __syncwarp();
-            const int w = diff - d.avrg_win;
+            const int w = diff - (a.avrg_dev ? __ldg(a.avrg_dev) : d.avrg_win);
             uint32_t agent_bits = 0;                // bit (q & 31) of lane (q >> 5): agent marked q
             for (int k = 0; k < n_log; k++) {
                 const uint32_t e = amaf_log[k];
@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         if (lane == 0) {
             if (a.diffs) a.diffs[g] = (int16_t)diff;
             if (!fault) {
-                const int w = diff - d.avrg_win;                     // AgentGo.cpp:327
+                const int w = diff - (a.avrg_dev ? __ldg(a.avrg_dev) : d.avrg_win);       // AgentGo.cpp:327
                 unsigned long long* c = (unsigned long long*)a.counters;
                 if (w >= 0) {                                        // sign test of AgentGo.cpp:328
                     atomicAdd(&c[s], 1ull);
