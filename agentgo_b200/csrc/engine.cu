@@ -160,11 +160,13 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     // (+9 % at 19x19), the warp kernel the lower LATENCY per playout (a warp serves one playout, not
     // four in lock step), so a launch of less than about two loads of the machine (100 playouts per SM)
     // finishes earlier on the warp kernel: 0.8 ms against 2.6 ms for 2 000 playouts at 19x19, equal at
-    // 32 000 (tests/latency_probe.py).  The reference's own genmove is 25 850 playouts.
+    // 32 000 (tests/latency_probe.py).  The reference's own genmove is 25 850 playouts.  On 9x9 a playout is
+    // 100 moves and the serial sections are short: the warp kernel wins at every size (20.2 M against 19.0 M
+    // playouts/s, profiles/r02_quick_bench.txt).
     int group_lanes = 0;
     if (!want_amaf) {
         if (cfg.kernel == AGB_KERNEL_GROUP8) group_lanes = 8;
-        else if (cfg.kernel == AGB_KERNEL_AUTO) group_lanes = local_units >= 2 * (int64_t)sm_count_ * 100 ? 8 : 0;
+        else if (cfg.kernel == AGB_KERNEL_AUTO) group_lanes = (local_units >= 2 * (int64_t)sm_count_ * 100 && board.n() > 9) ? 8 : 0;
         else if (cfg.kernel == AGB_KERNEL_GROUP16) group_lanes = 16;
         else if (cfg.kernel == AGB_KERNEL_GROUP32) group_lanes = 32;
     }
