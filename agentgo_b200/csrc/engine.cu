@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 namespace agb {
 
@@ -150,13 +151,12 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     int st;
     const bool thread_kernel = cfg.kernel == AGB_KERNEL_THREAD;
     if (want_amaf && thread_kernel)
-        return fail(AGB_ERR_INVALID, "AMAF marks are implemented by the warp kernel only");
+        return fail(AGB_ERR_INVALID, "AMAF marks are not implemented by the thread kernel");
     // this shard's share of the launch
     const int sh_rank = shard_units ? cfg.shard_rank : 0, sh_count = shard_units ? cfg.shard_count : 1;
     const int64_t total = (int64_t)S * P;
     const int64_t local_units = total > sh_rank ? (total - sh_rank + sh_count - 1) / sh_count : 0;
-    // Lanes per playout of the group kernel, 0 = another kernel.  AMAF marks are recorded by the warp
-    // kernel.  AGB_KERNEL_AUTO: the group kernel (four playouts per warp) has the higher THROUGHPUT
+    // Lanes per playout of the group kernel, 0 = another kernel.  AGB_KERNEL_AUTO: the group kernel (four playouts per warp) has the higher THROUGHPUT
     // (+9 % at 19x19), the warp kernel the lower LATENCY per playout (a warp serves one playout, not
     // four in lock step), so a launch of less than about two loads of the machine (100 playouts per SM)
     // finishes earlier on the warp kernel: 0.8 ms against 2.6 ms for 2 000 playouts at 19x19, equal at
@@ -164,12 +164,11 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     // 100 moves and the serial sections are short: the warp kernel wins at every size (20.2 M against 19.0 M
     // playouts/s, profiles/r02_quick_bench.txt).
     int group_lanes = 0;
-    if (!want_amaf) {
-        if (cfg.kernel == AGB_KERNEL_GROUP8) group_lanes = 8;
-        else if (cfg.kernel == AGB_KERNEL_AUTO) group_lanes = (local_units >= 2 * (int64_t)sm_count_ * 100 && board.n() > 9) ? 8 : 0;
-        else if (cfg.kernel == AGB_KERNEL_GROUP16) group_lanes = 16;
-        else if (cfg.kernel == AGB_KERNEL_GROUP32) group_lanes = 32;
-    }
+    const bool big = local_units >= 2 * (int64_t)sm_count_ * 100 && board.n() > 9;
+    if (cfg.kernel == AGB_KERNEL_GROUP8) group_lanes = 8;
+    else if (cfg.kernel == AGB_KERNEL_AUTO) group_lanes = big ? 8 : 0;
+    else if (cfg.kernel == AGB_KERNEL_GROUP16 && !want_amaf) group_lanes = 16;      // (the AMAF marks: 8 lanes per
+    else if (cfg.kernel == AGB_KERNEL_GROUP32 && !want_amaf) group_lanes = 32;      //  playout or the warp kernel)
     const size_t amaf_bytes = sizeof(long long) * (size_t)AGB_AMAF_WORDS(board.n()) * (size_t)amaf_classes();
     if (want_amaf) {
         if ((st = ensure(&d_amaf_, &cap_amaf_, amaf_bytes))) return st;
@@ -369,23 +368,43 @@ int Engine::playouts_batch(const agb_position* pos, int B, int64_t P, uint64_t s
                            uint32_t first_position_id, int64_t* wins, int64_t* sum_pos, int64_t* sum_neg,
                            int16_t* diffs, agb_stats* stats) {
     if (!pos || B <= 0 || P <= 0) return fail(AGB_ERR_INVALID, "bad batch");
-    std::vector<Position> starts;
-    std::vector<StartDesc> descs;
     std::vector<int> owner;     // batch index of each local start
-    HostBoard hb(board.n());
     for (int b = 0; b < B; b++) {
         const uint32_t pid = first_position_id + (uint32_t)b;
         if ((int)(pid % (uint32_t)cfg.shard_count) != cfg.shard_rank) continue;
-        hb.clear();
-        int st = hb.replay(pos[b].moves, pos[b].n_moves);
-        if (st) return fail(st == -2 ? AGB_ERR_OCCUPIED : AGB_ERR_INVALID, "bad move list in batch");
         const int colour = pos[b].to_move;
         if (colour != AGB_BLACK && colour != AGB_WHITE) return fail(AGB_ERR_INVALID, "bad to_move");
-        starts.push_back(hb.position());
-        StartDesc d = {pid, AGB_ROOT_CANDIDATE, (int16_t)colour, (int16_t)colour, 0, 0};
-        descs.push_back(d);
         owner.push_back(b);
     }
+    // The move lists are replayed on host threads (a position is defined by its move list: the orders
+    // the policy observes are history dependent), one HostBoard per thread, positions dealt round robin.
+    const int S0 = (int)owner.size();
+    std::vector<Position> starts((size_t)S0);
+    std::vector<StartDesc> descs((size_t)S0);
+    std::vector<int> bad((size_t)S0, 0);
+    {
+        const int n = board.n();
+        int nthreads = (int)std::thread::hardware_concurrency();
+        nthreads = std::max(1, std::min(std::min(nthreads, 16), S0 / 8));
+        auto work = [&](int t) {
+            HostBoard hb(n);
+            for (int s = t; s < S0; s += nthreads) {
+                const int b = owner[s];
+                hb.clear();
+                bad[s] = hb.replay(pos[b].moves, pos[b].n_moves);
+                starts[s] = hb.position();
+                const uint32_t pid = first_position_id + (uint32_t)b;
+                StartDesc d = {pid, AGB_ROOT_CANDIDATE, (int16_t)pos[b].to_move, (int16_t)pos[b].to_move, 0, 0};
+                descs[s] = d;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthreads; t++) th.emplace_back(work, t);
+        work(0);
+        for (std::thread& t : th) t.join();
+    }
+    for (int s = 0; s < S0; s++)
+        if (bad[s]) return fail(bad[s] == -2 ? AGB_ERR_OCCUPIED : AGB_ERR_INVALID, "bad move list in batch");
     for (int b = 0; b < B; b++) {
         if (wins) wins[b] = 0;
         if (sum_pos) sum_pos[b] = 0;

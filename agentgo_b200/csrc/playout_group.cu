@@ -13,9 +13,9 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_group_kerne
     grp::playout_group_body<C>(a, smem + (size_t)warp * C::warp_words, lane, (int)blockIdx.x * WARPS + warp);
 }
 
-template <int N, int G, int WARPS, int BLOCKS_PER_SM>
+template <int N, int G, int WARPS, int BLOCKS_PER_SM, bool AMAF = false>
 cudaError_t launch_g(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    typedef grp::GCfg<N, G, kJumpSteps> C;
+    typedef grp::GCfg<N, G, kJumpSteps, AMAF> C;
     static_assert(WARPS * BLOCKS_PER_SM * C::NG <= kGroupMaxPlayoutsPerSm, "elist_scratch is sized for 128 playouts per SM");
     const size_t smem = (size_t)WARPS * C::warp_words * sizeof(uint32_t);
     cudaError_t e = cudaFuncSetAttribute(playout_group_kernel<C, WARPS, BLOCKS_PER_SM>,
@@ -36,7 +36,16 @@ cudaError_t launch_playout_group(int n, int lanes, const KernelArgs& a, int sm_c
     // 8 lanes per playout: 100 playouts per SM (2 304 B of shared memory each at 19x19) in one block of
     // 25 warps, 80 registers; 16 lanes: 64 playouts in 32 warps of 64 registers; 32 lanes (the mapping
     // of playout_warp.cu run through this code, for comparison): 32 playouts in 32 warps.
-    if (lanes == 8) {
+    if (lanes == 8 && a.amaf) {
+        // with the AMAF log (160 B per playout): 88 playouts per SM, 22 warps of 88 registers
+        switch (n) {
+            case 9: return launch_g<9, 8, 22, 1, true>(a, sm_count, s, info);
+            case 13: return launch_g<13, 8, 22, 1, true>(a, sm_count, s, info);
+            case 19: return launch_g<19, 8, 22, 1, true>(a, sm_count, s, info);
+        }
+    } else if (a.amaf) {
+        return cudaErrorInvalidValue;       // the marks are recorded with 8 lanes per playout (or by the warp kernel)
+    } else if (lanes == 8) {
         switch (n) {
             case 9: return launch_g<9, 8, 24, 1>(a, sm_count, s, info);
             case 13: return launch_g<13, 8, 24, 1>(a, sm_count, s, info);

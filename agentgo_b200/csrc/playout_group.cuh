@@ -88,9 +88,13 @@ AGB_DEV uint32_t at(const uint32_t* w, uint32_t byte_off) {              // the 
     return *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(w) + byte_off);
 }
 
-template <int N_, int G_, int SEG_>
+// AMAF_: the playouts also record the first-play marks of MyWorker::work (AgentGo.cpp:289-290,304,319)
+// and accumulate KernelArgs::amaf (:329-338); candidate mode only.
+template <int N_, int G_, int SEG_, bool AMAF_ = false>
 struct GCfg {
     static constexpr int N = N_, G = G_, SEG = SEG_;
+    static constexpr bool AMAF = AMAF_;
+    static constexpr int kAmafLog = 80;             // first plays with cstep <= 40: at most 78
     static constexpr int W = N + 2, NP = W * W, NN = N * N, NG = 32 / G;
     static constexpr int BATCH = G * SEG;           // draws per refill of one playout
     static constexpr int R = 2 * BATCH;             // ring entries
@@ -100,7 +104,8 @@ struct GCfg {
     // cbuf: G 16-bit entries, the candidates of a move.  The stride from one playout of a warp to the next
     // is a multiple of 4 words (the ring is written with 128-bit stores) and = 8 mod 32, so that the
     // same field of the four playouts of a warp (cbuf, ring position, board word) sits in different banks.
-    static constexpr int words4 = ((oCbuf + G / 2 + 3) / 4) * 4;
+    static constexpr int oLog = oCbuf + G / 2;      // AMAF only: kAmafLog 16-bit entries
+    static constexpr int words4 = ((oLog + (AMAF ? kAmafLog / 2 : 0) + 3) / 4) * 4;
     static constexpr int words = words4 + ((8 - words4 % 32) + 32) % 32;
     static constexpr int warp_words = NG * words;
     static constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
@@ -430,6 +435,12 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
     GenState gs = {0, 0, 0, 0, 0};
     uint32_t unit = 0;          // which of this shard's units (the engine keeps a launch below 2^32 of them)
     bool fault = false;
+    // AMAF marks: a log of the first plays with cstep <= 40 (key = point | 512 for the agent's), resolved
+    // when the playout ends; cstep is 2 in the first pair (:293,:297)
+    constexpr int kAmafRange = 40;      // AMAF_RANGE, GoContest/AgentGo.h:16
+    uint16_t* const amaf_log = reinterpret_cast<uint16_t*>(gsm + C::oLog);
+    int n_log = 0, cstep = 2;
+    uint32_t amaf_agent = 0;
 
 #pragma unroll 1
     for (;;) {
@@ -451,6 +462,33 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 const bool xfault = __shfl_sync(kFull, (int)fault, src) != 0;
                 const StartDesc d = a.descs[xs];
                 const int diff = xfault ? -32768 : score_diff<C>(xw, (uint32_t)d.agent, lane);
+                if (C::AMAF && !xfault) {
+                    // :329-338 — point q counts for the agent table when the agent's first play there has
+                    // cstep <= 40, else for the enemy table when the enemy's has (the `else if`)
+                    const uint16_t* xlog = reinterpret_cast<const uint16_t*>(xsm + C::oLog);
+                    const int xn = __shfl_sync(kFull, n_log, src);
+                    const int wv = diff - (a.avrg_dev ? *a.avrg_dev : d.avrg_win);
+                    uint32_t agent_bits = 0;                // bit (q & 31) of lane (q >> 5): the agent marked q
+#pragma unroll 1
+                    for (int k = 0; k < xn; k++) {
+                        const uint32_t e = xlog[k];
+                        if ((e & 512u) && lane == (int)((e & 511u) >> 5)) agent_bits |= 1u << (e & 31u);
+                    }
+#pragma unroll 1
+                    for (int b0 = 0; b0 < xn; b0 += 32) {
+                        const bool valid = b0 + lane < xn;
+                        const uint32_t e = valid ? xlog[b0 + lane] : 0u;
+                        const uint32_t q = e & 511u;
+                        const bool is_agent = (e & 512u) != 0;
+                        const bool agent_marked = (__shfl_sync(kFull, agent_bits, (int)(q >> 5)) >> (q & 31u)) & 1u;
+                        if (valid && wv != 0 && (is_agent || !agent_marked)) {
+                            const uint32_t row = q / W - 1, col = q % W - 1;
+                            const uint32_t slot = ((is_agent ? 0u : 2u) + (wv < 0 ? 1u : 0u)) * (kAmafRange + 1) + (e >> 10);
+                            atomicAdd((unsigned long long*)&a.amaf[((size_t)d.amaf_class * (4 * (kAmafRange + 1)) + slot) * C::NN + row * C::N + col],
+                                      (unsigned long long)(long long)wv);
+                        }
+                    }
+                }
                 if (lane == 0) {
                     atomicAdd(&a.stats[kStatMoves], (unsigned long long)xmv);
                     atomicAdd(&a.stats[kStatDraws], (unsigned long long)xpos);
@@ -510,6 +548,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     pos = 0; mv = 0;
                     gs.g0 = t.s0; gs.g1 = t.s1; gs.g2 = t.s2; gs.g3 = t.s3; gs.gen_end = 0;
                     unit = (uint32_t)l; fault = false;
+                    n_log = 0; cstep = 2; amaf_agent = (uint32_t)d.agent;
                 }
             } else if (grp == X) {
                 phase = kDone;
@@ -836,6 +875,26 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
             }
         }
 
+        // ---- AMAF: mark[r] / mark2[r] = cstep of the FIRST play of that side at r (:304,:319) ----
+        if (C::AMAF) {
+            const bool logging = doput && cstep <= kAmafRange;      // only cstep <= AMAF_RANGE is ever used
+            if (__any_sync(kFull, logging)) {
+                const uint32_t key = (uint32_t)(r < 0 ? 0 : r) | (colour == amaf_agent ? 512u : 0u);
+                bool dup = false;
+#pragma unroll 1
+                for (int b0 = 0; __any_sync(kFull, logging && b0 < n_log); b0 += G) {
+                    const uint32_t e = b0 + gl < n_log ? amaf_log[b0 + gl] : 0xffffu;
+                    const unsigned hitm = (__ballot_sync(kFull, (e & 1023u) == key) >> gbase) & C::GM;      // (no `||`: every lane votes)
+                    dup = dup || hitm != 0;
+                }
+                if (logging && !dup) {
+                    if (gl == 0) amaf_log[n_log] = (uint16_t)(key | ((uint32_t)cstep << 10));
+                    n_log++;
+                }
+                __syncwarp();
+            }
+        }
+
         // ---- pair loop of MyWorker::work (AgentGo.cpp:295-325) / testAvrgWin (:422-443) ----
         // The move that closes a pair (the second mover's) ends the playout when neither side moved:
         // the first mover's move is what prev still holds, -1 for a pass.
@@ -845,6 +904,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
             if (closes) {
                 if ((before & r) < 0) phase = kEnded;
                 else if ((int)mv > a.max_moves) { fault = true; phase = kEnded; }   // fault detector, once per pair
+                if (C::AMAF) cstep++;
             }
             colour = 3u - colour;
             closes = !closes;

@@ -44,6 +44,15 @@ void run(const KernelArgs& a) {
 
 template <int G>
 int dispatch(int n, const KernelArgs& a) {
+    if (a.amaf) {
+        if (G != 8) return -1;
+        switch (n) {
+            case 9: run<grp::GCfg<9, 8, kJumpSteps, true>>(a); return 0;
+            case 13: run<grp::GCfg<13, 8, kJumpSteps, true>>(a); return 0;
+            case 19: run<grp::GCfg<19, 8, kJumpSteps, true>>(a); return 0;
+        }
+        return -1;
+    }
     switch (n) {
         case 9: run<grp::GCfg<9, G, kJumpSteps>>(a); return 0;
         case 13: run<grp::GCfg<13, G, kJumpSteps>>(a); return 0;
@@ -56,11 +65,12 @@ int dispatch(int n, const KernelArgs& a) {
 
 // P playouts of one start (root mode: cand_row < 0; candidate mode: the candidate is played and
 // the other side moves first), like tests/csrc/host_sim.cpp.  out3 = wins, sum_pos, sum_neg;
-// stat4 = moves, draws, faults, playouts.  Returns the number of collectives run (>= 0) or -1.
+// stat4 = moves, draws, faults, playouts; amaf (may be NULL, candidate mode, 8 lanes): the AMAF table the
+// playouts accumulate into.  Returns the number of collectives run (>= 0) or -1.
 extern "C" long long emu_group_playouts(int n, int lanes, const uint32_t* moves, int n_moves, int colour,
                                         int cand_row, int cand_col, uint32_t position_id, uint32_t cand_idx,
                                         int64_t P, uint64_t seed_base, int avrg_win, int max_moves,
-                                        int16_t* diffs, int64_t* out3, int64_t* stat4) {
+                                        int16_t* diffs, int64_t* out3, int64_t* stat4, int64_t* amaf) {
     HostBoard hb(n);
     if (hb.replay(moves, n_moves)) return -1;
     Position start = hb.position();
@@ -93,6 +103,7 @@ extern "C" long long emu_group_playouts(int n, int lanes, const uint32_t* moves,
     a.work_counter = &work;
     a.counters = counters;
     a.diffs = diffs;
+    a.amaf = (long long*)amaf;      // [2 which][2 sign][41 step][n*n] or NULL; candidate mode
     a.stats = stats;
     a.rng = prm;
     a.max_moves = max_moves > 0 ? max_moves : kDefaultMaxMoves;

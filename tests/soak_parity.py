@@ -1,7 +1,7 @@
 """One-off parity soak (not part of the default suites): many random positions of every length,
 ALL empty points as candidates (including suicides and ko points), both colours, the group kernel
-(8 lanes per playout: AGB_KERNEL_AUTO's choice for large launches) and, for the AMAF marks, the warp
-kernel against the oracle.  usage: python tests/soak_parity.py [positions] [P]"""
+(8 lanes per playout: AGB_KERNEL_AUTO's choice for large launches), AMAF marks included, against the
+oracle.  usage: python tests/soak_parity.py [positions] [P]"""
 import json
 import sys
 import time
@@ -33,7 +33,7 @@ for k in range(NPOS):
     r = e.playouts(colour, None, 4 * P, seed_base=k, position_id=k, want_diffs=True)
     orr = ob.playouts(colour, None, 4 * P, seed_base=k, position_id=k, threads=0)
     good = (d == od).all() and (w == ow).all() and (sp == osp).all() and (sn == osn).all() and (r[3] == orr[3]).all()
-    a = ag.Engine(n).replay(mv).playouts_amaf(colour, cands[:12], P, avrg_win=avrg, seed_base=k)
+    a = e.playouts_amaf(colour, cands[:12], P, avrg_win=avrg, seed_base=k)
     oa = ob.playouts_amaf(colour, cands[:12], P, avrg_win=avrg, seed_base=k)
     good = good and (a[3] == oa[3]).all()
     total += len(cands) * P + 4 * P

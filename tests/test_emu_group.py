@@ -33,6 +33,25 @@ def test_candidates_golden(lanes):
         assert (o[0], o[1], o[2]) == (g["wins"][ci], g["sum_pos"][ci], g["sum_neg"][ci])
 
 
+def test_amaf_marks_match_oracle(port_lib):
+    """The first-play marks (AgentGo.cpp:289-290,304,319,329-338) recorded by the group kernel, against
+    the oracle's restatement of the reference's loop, candidate by candidate."""
+    emu = emu_group()
+    po = port_lib
+    for n, nmoves, P in ((9, 20, 24), (13, 60, 12)):
+        mv = po.OracleBoard(n, "port").random_game(1, nmoves, 4711 + n)
+        ob = po.OracleBoard(n, "port").replay(mv)
+        st = ob.export_state()
+        empties = [i for i in range(n * n) if st[16 + i] == 0]
+        cands = [(i // n, i % n) for i in empties[::max(1, len(empties) // 4)]][:4]
+        ow, osp, osn, oa = ob.playouts_amaf(2, cands, P, avrg_win=2, seed_base=31, position_id=5, per_candidate=True)
+        for ci, c in enumerate(cands):
+            amaf = np.zeros((2, 2, 41, n * n), dtype=np.int64)
+            o, d, s, _ = emu_playouts(emu, n, 8, mv, 2, c, P, avrg_win=2, seed_base=31, position_id=5, cand_idx=ci, amaf=amaf)
+            assert (o[0], o[1], o[2]) == (ow[ci], osp[ci], osn[ci])
+            assert (amaf == oa[ci]).all() and amaf.any()
+
+
 def test_midgame_golden():
     emu = emu_group()
     g = golden("midgame_19.npz")

@@ -206,8 +206,10 @@ def test_full_size_config2_bit_exact(built_lib):
     assert st["moves"] == ost["moves"] and st["rng_draws"] == ost["rng_draws"]
 
 
-def test_amaf_marks_match_oracle(built_lib):
-    """'next' row 1: AMAF first-play marks, integer contract of agb_playouts_amaf."""
+@pytest.mark.parametrize("kernel", [ag.KERNEL_WARP, ag.KERNEL_GROUP8])
+def test_amaf_marks_match_oracle(built_lib, kernel):
+    """'next' row 1: AMAF first-play marks, integer contract of agb_playouts_amaf, by both
+    kernels that record them (the warp kernel and the group kernel with 8 lanes per playout)."""
     for n, P in ((9, 200), (13, 120), (19, 80)):
         mv = po.OracleBoard(n, "best").random_game(1, n * n // 3, 321)
         ob = po.OracleBoard(n, "best").replay(mv)
@@ -215,7 +217,7 @@ def test_amaf_marks_match_oracle(built_lib):
         emp = [i for i in range(n * n) if st[16 + i] == 0][::5][:9]
         cands = [(i // n, i % n) for i in emp]
         ow, osp, osn, oa = ob.playouts_amaf(2, cands, P, avrg_win=1, seed_base=5, position_id=2)
-        e = ag.Engine(n).replay(mv)
+        e = ag.Engine(n, kernel=kernel).replay(mv)
         w, sp, sn, a, stt = e.playouts_amaf(2, cands, P, avrg_win=1, seed_base=5, position_id=2)
         assert (w == ow).all() and (sp == osp).all() and (sn == osn).all()
         assert (a == oa).all(), np.argwhere(a != oa)[:5]

@@ -84,7 +84,7 @@ def emu_group():
 
 
 def emu_playouts(emu, n, lanes, moves, colour, cand, P, avrg_win=0, seed_base=20151001, position_id=0,
-                 cand_idx=0, max_moves=0):
+                 cand_idx=0, max_moves=0, amaf=None):
     mv = np.ascontiguousarray(moves, dtype=np.uint32)
     d = np.zeros(P, dtype=np.int16)
     o = np.zeros(3, dtype=np.int64)
@@ -93,6 +93,6 @@ def emu_playouts(emu, n, lanes, moves, colour, cand, P, avrg_win=0, seed_base=20
                                cand[0] if cand is not None else -1, cand[1] if cand is not None else -1,
                                C.c_uint32(position_id), C.c_uint32(cand_idx), C.c_int64(P), C.c_uint64(seed_base),
                                avrg_win, max_moves, d.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p),
-                               s.ctypes.data_as(C.c_void_p))
+                               s.ctypes.data_as(C.c_void_p), amaf.ctypes.data_as(C.c_void_p) if amaf is not None else None)
     assert r >= 0
     return o, d, s, r
