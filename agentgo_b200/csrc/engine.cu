@@ -123,7 +123,7 @@ Engine::~Engine() {
         if (t.ev0) cudaEventDestroy(t.ev0);
         if (t.ev1) cudaEventDestroy(t.ev1);
     }
-    cudaFree(d_diffs_); cudaFree(d_gather_); cudaFree(d_elist_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_amaf_);
+    cudaFree(d_diffs_); cudaFree(d_gather_); cudaFree(d_elist_); cudaFree(d_jump_); cudaFree(d_jump_bytes_); cudaFree(d_jump_batch_); cudaFree(d_amaf_);
     cudaFree(d_avrg_);
     if (stream_) cudaStreamDestroy(stream_);
 }
@@ -217,8 +217,16 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
             build_jump_bytes(prm, group_lanes, kJumpSteps, jb.data());
             if ((st = ensure(&d_jump_bytes_, &cap_jump_bytes_, jump_bytes_size(group_lanes)))) return st;
             AGB_CUDA(cudaMemcpy(d_jump_bytes_, jb.data(), jump_bytes_size(group_lanes), cudaMemcpyHostToDevice));
+            JumpTable* jt = new JumpTable;
+            build_jump(prm, group_lanes * kJumpSteps, jt);      // T^BATCH, the step of every lane from batch to batch
+            st = ensure(&d_jump_batch_, &cap_jump_batch_, sizeof(JumpTable));
+            cudaError_t ce = st ? cudaSuccess : cudaMemcpy(d_jump_batch_, jt, sizeof(JumpTable), cudaMemcpyHostToDevice);
+            delete jt;
+            if (st) return st;
+            if (ce != cudaSuccess) return cuda_fail(ce, "cudaMemcpy (jump table)");
             jump_bytes_lanes_ = group_lanes;
         }
+        a.jump_batch = (const JumpTable*)d_jump_batch_;
         a.jump_bytes = (const uint4*)d_jump_bytes_;
         // the empty-point arrays of the resident playouts (global memory, kernel_args.h)
         if ((st = ensure(&d_elist_, &cap_elist_, (size_t)sm_count_ * kGroupMaxPlayoutsPerSm * kGroupElistCap * sizeof(uint16_t)))) return st;

@@ -92,6 +92,7 @@ private:
     Slot& sl() { return slot_[cur_]; }
     void* d_jump_ = nullptr;             // JumpTable (TinyMT32 T^16), built at create time
     void* d_jump_bytes_ = nullptr; size_t cap_jump_bytes_ = 0;   // JumpBytes of the group kernel
+    void* d_jump_batch_ = nullptr; size_t cap_jump_batch_ = 0;   // its T^BATCH nibble table (goes to shared memory)
     void* d_elist_ = nullptr; size_t cap_elist_ = 0;   // group kernel: empty-point arrays of the resident playouts
     int jump_bytes_lanes_ = 0;           // lanes per playout d_jump_bytes_ was built for
     void* d_diffs_ = nullptr; size_t cap_diffs_ = 0;

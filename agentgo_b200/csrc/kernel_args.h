@@ -99,6 +99,7 @@ struct KernelArgs {
     const GroupPosition* gstarts;   // [n_starts] device (group kernel)
     const JumpTable* jump;      // device (warp kernel)
     const uint4* jump_bytes;    // device (group kernel), JumpBytes for the launch's lanes per playout
+    const JumpTable* jump_batch; // device (group kernel): T^(lanes*SEG) split by nibble, copied to shared memory
     uint16_t* elist_scratch;    // device (group kernel): kGroupElistCap entries per resident playout
     const StartDesc* descs;     // [n_starts] device
     int32_t n_starts;

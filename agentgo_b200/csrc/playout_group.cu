@@ -10,14 +10,19 @@ template <class C, int WARPS, int BLOCKS_PER_SM>
 __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_group_kernel(const KernelArgs a) {
     extern __shared__ __align__(16) uint32_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    grp::playout_group_body<C>(a, smem + (size_t)warp * C::warp_words, lane, (int)blockIdx.x * WARPS + warp);
+    // behind the playouts: the jump matrix T^BATCH of the refills (8 KB, read by every warp of the block)
+    uint4* tab = reinterpret_cast<uint4*>(smem + (size_t)WARPS * C::warp_words);
+    for (int i = threadIdx.x; i < 32 * 16; i += WARPS * 32) tab[i] = a.jump_batch->e[i];
+    __syncthreads();
+    grp::playout_group_body<C>(a, smem + (size_t)warp * C::warp_words, lane, (int)blockIdx.x * WARPS + warp, tab);
 }
 
 template <int N, int G, int WARPS, int BLOCKS_PER_SM, bool AMAF = false>
 cudaError_t launch_g(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
     typedef grp::GCfg<N, G, kJumpSteps, AMAF> C;
     static_assert(WARPS * BLOCKS_PER_SM * C::NG <= kGroupMaxPlayoutsPerSm, "elist_scratch is sized for 128 playouts per SM");
-    const size_t smem = (size_t)WARPS * C::warp_words * sizeof(uint32_t);
+    static_assert(C::warp_words % 4 == 0, "the jump table behind the playouts is 16-byte aligned");
+    const size_t smem = (size_t)WARPS * C::warp_words * sizeof(uint32_t) + sizeof(JumpTable);
     cudaError_t e = cudaFuncSetAttribute(playout_group_kernel<C, WARPS, BLOCKS_PER_SM>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -37,11 +42,11 @@ cudaError_t launch_playout_group(int n, int lanes, const KernelArgs& a, int sm_c
     // 25 warps, 80 registers; 16 lanes: 64 playouts in 32 warps of 64 registers; 32 lanes (the mapping
     // of playout_warp.cu run through this code, for comparison): 32 playouts in 32 warps.
     if (lanes == 8 && a.amaf) {
-        // with the AMAF log (160 B per playout): 88 playouts per SM, 22 warps of 88 registers
+        // with the AMAF log (160 B per playout): 84 playouts per SM, 21 warps of 96 registers
         switch (n) {
-            case 9: return launch_g<9, 8, 22, 1, true>(a, sm_count, s, info);
-            case 13: return launch_g<13, 8, 22, 1, true>(a, sm_count, s, info);
-            case 19: return launch_g<19, 8, 22, 1, true>(a, sm_count, s, info);
+            case 9: return launch_g<9, 8, 21, 1, true>(a, sm_count, s, info);
+            case 13: return launch_g<13, 8, 21, 1, true>(a, sm_count, s, info);
+            case 19: return launch_g<19, 8, 21, 1, true>(a, sm_count, s, info);
         }
     } else if (a.amaf) {
         return cudaErrorInvalidValue;       // the marks are recorded with 8 lanes per playout (or by the warp kernel)

@@ -220,35 +220,32 @@ AGB_DEV uint4 jump_lookup(const uint4* __restrict__ tab, uint32_t g0, uint32_t g
     return t;
 }
 template <class C>
-AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* __restrict__ jb, int gl) {
-    static_assert(C::SEG % 8 == 0, "four quarters of an even number of draws");
-    TinyMT mine;
-    mine.s0 = st.g0; mine.s1 = st.g1; mine.s2 = st.g2; mine.s3 = st.g3;
-    uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
+AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* tab, int gl) {
+    // tab: T^BATCH split by state NIBBLE (JumpTable: entry l*16 + v is the image of nibble l having value
+    // v), 8 KB in SHARED memory — the byte-split matrix in L2 cost 16 lookups instead of 32, but their
+    // latency was 5 % of all stall samples and their traffic 2.9 TB/s
     uint4 t = make_uint4(0, 0, 0, 0);
-    // four quarters: the lookups of a quarter of the state's bytes (matrix 0: T^BATCH) are issued, a
-    // quarter of the segment is generated while they are on their way from L2, then they are folded in
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {       // (rolled: eight 128-bit loads in flight are what the registers hold)
         const uint32_t word = q == 0 ? st.g0 : (q == 1 ? st.g1 : (q == 2 ? st.g2 : st.g3));
-        const uint4 u0 = __ldg(jb + (4 * q + 0) * 256 + (word & 255u));
-        const uint4 u1 = __ldg(jb + (4 * q + 1) * 256 + ((word >> 8) & 255u));
-        const uint4 u2 = __ldg(jb + (4 * q + 2) * 256 + ((word >> 16) & 255u));
-        const uint4 u3 = __ldg(jb + (4 * q + 3) * 256 + (word >> 24));
-        if (part) {     // (no collective inside: the lanes of a group that does not take part just wait)
 #pragma unroll
-            for (int j = 0; j < C::SEG / 8; j++) {
-                mine.next_state(prm.mat1, prm.mat2);
-                const uint32_t lo = mine.temper(prm.tmat) >> 17;
-                mine.next_state(prm.mat1, prm.mat2);
-                const uint32_t hi = mine.temper(prm.tmat) >> 17;
-                out[q * (C::SEG / 8) + j] = lo | (hi << 16);
-            }
+        for (int k = 0; k < 8; k++) {
+            const uint4 u = tab[(8 * q + k) * 16 + ((word >> (4 * k)) & 15u)];
+            t.x ^= u.x; t.y ^= u.y; t.z ^= u.z; t.w ^= u.w;
         }
-        t.x ^= u0.x ^ u1.x ^ u2.x ^ u3.x; t.y ^= u0.y ^ u1.y ^ u2.y ^ u3.y;
-        t.z ^= u0.z ^ u1.z ^ u2.z ^ u3.z; t.w ^= u0.w ^ u1.w ^ u2.w ^ u3.w;
     }
-    if (part) {
+    if (part) {         // (no collective inside: the lanes of a group that does not take part just wait)
+        TinyMT mine;
+        mine.s0 = st.g0; mine.s1 = st.g1; mine.s2 = st.g2; mine.s3 = st.g3;
+        uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
+#pragma unroll 2
+        for (int j = 0; j < C::SEG / 2; j++) {
+            mine.next_state(prm.mat1, prm.mat2);
+            const uint32_t lo = mine.temper(prm.tmat) >> 17;
+            mine.next_state(prm.mat1, prm.mat2);
+            const uint32_t hi = mine.temper(prm.tmat) >> 17;
+            out[j] = lo | (hi << 16);
+        }
         st.g0 = t.x; st.g1 = t.y; st.g2 = t.z; st.g3 = t.w;
         st.gen_end += (uint32_t)C::BATCH;
     }
@@ -394,7 +391,7 @@ AGB_DEV int score_diff(const uint32_t* w, uint32_t agent, int lane) {
 
 // ---- the kernel body ----------------------------------------------------------------------------
 template <class C>
-AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int lane, int warp_slot) {
+AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int lane, int warp_slot, const uint4* jump_tab) {
     constexpr int G = C::G, W = C::W;
     constexpr uint32_t RM = (uint32_t)(C::R - 1);
     const int gl = lane & (G - 1);
@@ -560,7 +557,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
 #define AGB_ENSURE(needpred, k)                                                                     \
         if (__any_sync(kFull, (needpred) && gs.gen_end - pos < (uint32_t)(k))) {                     \
             const bool part_ = live && gs.gen_end - pos <= (uint32_t)(C::R - C::BATCH);              \
-            gs = refill<C>(part_, ring, gs, a.rng, jt, gl);                                   \
+            gs = refill<C>(part_, ring, gs, a.rng, jump_tab, gl);                                   \
         }
 
         // ---- Board::getRandomPiece, Board.cpp:341-411 ----

@@ -20,12 +20,13 @@ template <class C>
 struct Job {
     KernelArgs a;
     uint32_t* smem;
+    const uint4* tab;
 };
 
 template <class C>
 void lane_entry(int lane, void* user) {
     Job<C>* j = (Job<C>*)user;
-    grp::playout_group_body<C>(j->a, j->smem, lane, 0);
+    grp::playout_group_body<C>(j->a, j->smem, lane, 0, j->tab);
 }
 
 template <class C>
@@ -38,6 +39,7 @@ void run(const KernelArgs& a) {
     j.smem = smem;
     std::vector<uint16_t> scratch((size_t)C::NG * C::E, 0xdeadu);      // the warp's empty-point arrays (global memory)
     j.a.elist_scratch = scratch.data();
+    j.tab = a.jump_batch->e;        // (in shared memory on the GPU)
     emu::run_warp(&lane_entry<C>, &j);
     free(smem);
 }
@@ -93,6 +95,9 @@ extern "C" long long emu_group_playouts(int n, int lanes, const uint32_t* moves,
     memset(&a, 0, sizeof(a));
     a.gstarts = &gp;
     a.jump_bytes = jb.data();
+    JumpTable jt;
+    build_jump(prm, lanes * kJumpSteps, &jt);
+    a.jump_batch = &jt;
     a.descs = &d;
     a.n_starts = 1;
     a.counter_stride = 1;
