@@ -16,6 +16,16 @@
 //    converged code — no divergent collectives, none of the BSSY/BSYNC/WARPSYNC scaffolding the
 //    compiler had to put around the collectives of the warp kernel.  tests/csrc/simt_emu.h runs
 //    this very source on the CPU and aborts if any lane reaches a collective at another site.
+//    CONVERGENCE NOTE.  ptxas has to PROVE the convergence, or it guards every collective of the kernel
+//    with UMOV + BRA.DIV and a WARPSYNC.COLLECTIVE slow path (8 % of the executed instructions, a
+//    quarter of the code).  Two things defeated the proof and are avoided (found by cutting the kernel
+//    down until the guards went away, profiles/r02_convergence.txt): (1) a loop whose body ENDS in a
+//    lane-dependent `if` gets two back edges, one of them out of divergent code, and the loop header —
+//    hence everything in the loop — counts as divergent: such loops end in a __syncwarp() (a NOP once
+//    convergence is proven), which gives them a single latch behind the reconvergence point; (2) values
+//    that are warp-uniform by construction but arrive through a shuffle, shared memory or a function
+//    argument make the branches on them "divergent": they are passed through a redux (its result is
+//    a uniform register) or the branch is taken on a vote.
 //  * RARE BULK WORK BORROWS THE WHOLE WARP.  Clone, scoring, complex mode
 //    (Board::getRandomPieceComplex) and the compaction of the empty-point array serve one group at
 //    a time with all 32 lanes (the board of any group of the warp is in reach of every lane).
@@ -299,6 +309,11 @@ template <class C>
 AGB_NOINLINE int complex_pick(uint32_t* w, uint16_t* elist, int n_el, int spaces, uint32_t agent, int ko_key,
                               uint32_t draw, int lane, int* used) {
     constexpr int kKeep = 2;
+    // The arguments are the same in all lanes, but the compiler cannot see that through the call: a redux
+    // puts them in uniform registers, and every branch below becomes a uniform branch (convergence note).
+    n_el = (int)__reduce_max_sync(kFull, (unsigned)n_el);
+    spaces = (int)__reduce_max_sync(kFull, (unsigned)spaces);
+    draw = __reduce_max_sync(kFull, draw);
     uint32_t ents[kKeep];
 #pragma unroll
     for (int r = 0; r < kKeep; r++) {
@@ -867,6 +882,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                         if (single) ko_key = (int)(((3u - colour) << 16) | kcur);   // :328-333
                         kcur = nxk;
                     }
+                    __syncwarp();   // one latch (convergence note)
                 }
                 __syncwarp();
             }
@@ -906,6 +922,8 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
             colour = 3u - colour;
             closes = !closes;
         }
+        // (see the convergence note at the top of the file: one latch for the loop)
+        __syncwarp();
 #undef AGB_ENSURE
     }
 }
