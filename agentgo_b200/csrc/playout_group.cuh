@@ -63,6 +63,14 @@
 #define AGB_NOINLINE __device__ __noinline__
 #endif
 
+// tunables of the move selection (measured: profiles/r02_tuning.txt)
+#ifndef AGB_KSCAN
+#define AGB_KSCAN 32
+#endif
+#ifndef AGB_KWANT
+#define AGB_KWANT 3
+#endif
+
 namespace agb {
 namespace grp {
 
@@ -206,18 +214,20 @@ AGB_DEV Ev eval_point(const uint32_t* w, uint32_t agent, int idx, int ko_key) {
 }
 
 // ---- rand(): ring refill ------------------------------------------------------------------------
-// The next BATCH = G*SEG draws of the playouts that take part (`part`, a per-group predicate).
-// Lane j of a playout's G lanes generates draws [j*SEG, (j+1)*SEG) of every batch, and keeps for
-// that a generator state of its OWN: the state its segment of the next batch starts from.  TinyMT32's
-// transition is linear over GF(2), so that state moves from one batch to the next by the same
-// matrix for every lane, T^BATCH: 16 byte-table lookups (JumpBytes, matrix 0), no other lane
-// involved.  The lookups depend only on the state the segment starts from, so they are issued first
-// and their latency (the table lives in L2) is covered by generating the segment.  When a playout
-// is set up lane j jumps from the seed state by T^(SEG*j) (matrix j).  Groups that do not take
-// part run along and store nothing.
+// Lane j of a playout's G lanes generates draws [j*SEG, (j+1)*SEG) of every batch of BATCH = G*SEG, and
+// keeps for that a generator state of its OWN: the state its NEXT segment starts from.  TinyMT32's
+// transition is linear over GF(2), so that state moves from one batch to the next by the same matrix
+// for every lane, T^BATCH (a nibble table in shared memory), no other lane involved.  When a playout is
+// set up lane j jumps from the seed state by T^(SEG*j) (matrix j of JumpBytes).
+// A refill TOPS UP every live playout of the warp, segment by segment: a lane generates its next segment
+// iff the ring has room for it (the slots it overwrites hold consumed draws), so the frontier gen_end of a
+// playout moves to the last segment boundary the ring can hold, whatever the playout had left.  (Batches
+// taken or left as a whole served 1.8 of the 4 playouts per call: the one that ran dry and those that
+// happened to have half a ring free.  The call costs the same for any number of takers.)
 struct GenState {
-    uint32_t g0, g1, g2, g3;    // this lane's state at draw gen_end + SEG * (lane in group)
-    uint32_t gen_end;           // draws [pos, gen_end) of the playout are in the ring
+    uint32_t g0, g1, g2, g3;    // this lane's state at the start of its next segment: the first draw at or
+                                // after gen_end that is SEG * (lane in group) modulo BATCH
+    uint32_t gen_end;           // draws [pos, gen_end) of the playout are in the ring; a multiple of SEG
 };
 AGB_DEV uint4 jump_lookup(const uint4* __restrict__ tab, uint32_t g0, uint32_t g1, uint32_t g2, uint32_t g3) {
     uint4 t = make_uint4(0, 0, 0, 0);
@@ -230,7 +240,13 @@ AGB_DEV uint4 jump_lookup(const uint4* __restrict__ tab, uint32_t g0, uint32_t g
     return t;
 }
 template <class C>
-AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams prm, const uint4* tab, int gl) {
+AGB_NOINLINE GenState refill(bool live, uint32_t pos, uint16_t* ring, GenState st, RngParams prm, const uint4* tab, int gl) {
+    // this lane's next segment, and how far the ring can be filled: a segment at s needs s + SEG <= pos + R;
+    // at most one segment per lane and call
+    const uint32_t mine_at = st.gen_end + (((uint32_t)(C::SEG * gl) - st.gen_end) & (uint32_t)(C::BATCH - 1));
+    // (gen_end <= pos + R and is a multiple of SEG, so the boundary below is never behind it)
+    const uint32_t frontier = min((pos + (uint32_t)C::R) & ~(uint32_t)(C::SEG - 1), st.gen_end + (uint32_t)C::BATCH);
+    const bool part = live && mine_at < frontier;
     // tab: T^BATCH split by state NIBBLE (JumpTable: entry l*16 + v is the image of nibble l having value
     // v), 8 KB in SHARED memory — the byte-split matrix in L2 cost 16 lookups instead of 32, but their
     // latency was 5 % of all stall samples and their traffic 2.9 TB/s
@@ -247,7 +263,7 @@ AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams p
     if (part) {         // (no collective inside: the lanes of a group that does not take part just wait)
         TinyMT mine;
         mine.s0 = st.g0; mine.s1 = st.g1; mine.s2 = st.g2; mine.s3 = st.g3;
-        uint32_t* out = reinterpret_cast<uint32_t*>(ring + (st.gen_end & (uint32_t)(C::R - 1)) + gl * C::SEG);
+        uint32_t* out = reinterpret_cast<uint32_t*>(ring + (mine_at & (uint32_t)(C::R - 1)));
 #pragma unroll 2
         for (int j = 0; j < C::SEG / 2; j++) {
             mine.next_state(prm.mat1, prm.mat2);
@@ -257,8 +273,8 @@ AGB_NOINLINE GenState refill(bool part, uint16_t* ring, GenState st, RngParams p
             out[j] = lo | (hi << 16);
         }
         st.g0 = t.x; st.g1 = t.y; st.g2 = t.z; st.g3 = t.w;
-        st.gen_end += (uint32_t)C::BATCH;
     }
+    if (live) st.gen_end = frontier;
     __syncwarp();
     return st;
 }
@@ -571,8 +587,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
 
 #define AGB_ENSURE(needpred, k)                                                                     \
         if (__any_sync(kFull, (needpred) && gs.gen_end - pos < (uint32_t)(k))) {                     \
-            const bool part_ = live && gs.gen_end - pos <= (uint32_t)(C::R - C::BATCH);              \
-            gs = refill<C>(part_, ring, gs, a.rng, jump_tab, gl);                                   \
+            gs = refill<C>(live, pos, ring, gs, a.rng, jump_tab, gl);                               \
         }
 
         // ---- Board::getRandomPiece, Board.cpp:341-411 ----
@@ -598,8 +613,8 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
         // and for the first move of a playout that was settled when it was set up.)
         const bool nbact = search && prev >= 0;
         {
-            constexpr int kScan = 32;           // pairs looked at per pass at most (their index has 5 bits in an item)
-            constexpr int kWant = 3;            // ... until the pass holds this many rejection candidates: one
+            constexpr int kScan = AGB_KSCAN;    // pairs looked at per pass at most (their index has 5 bits in an item)
+            constexpr int kWant = AGB_KWANT;            // ... until the pass holds this many rejection candidates: one
                                                 // more scan round costs a fifth of one more pass
             int lim = kEndingThreshold - 1;     // rejection pairs that may still be accepted: the 100th draw is
                                                 // consumed but never accepted (:402-405)
