@@ -112,6 +112,16 @@ __device__ __forceinline__ uint32_t pack0(int a, int b, int col) {
 }
 // high half of a stone's word: colour and next-in-string link
 __device__ __forceinline__ uint16_t packHi(int b, int col) { return (uint16_t)(((uint32_t)b << 2) | ((uint32_t)col << 14)); }
+// CONVERGENCE.  The scalars of a playout (the move, the position in the rand() stream, walk cursors) hold
+// the same value in all 32 lanes, but ptxas cannot see that once they have been through a shuffle or
+// shared memory: a branch on them counts as divergent, and then EVERY collective of the kernel gets a
+// UMOV + BRA.DIV guard and a WARPSYNC.COLLECTIVE slow path (15 % of the executed instructions, a third
+// of the code).  uni() takes the branch on a vote, which is provably uniform.  The sites below are the
+// minimal set (found by removing them one at a time while the kernel stayed free of BRA.DIV); together
+// with the __syncwarp() that ends the playout loop — it gives the loop a single latch behind the
+// lane-0 epilogue — they take the 19x19 kernel from 2 496 to 1 560 SASS instructions
+// (tests/test_sass_convergence.py keeps it that way).
+__device__ __forceinline__ bool uni(bool p) { return __any_sync(kFull, p) != 0; }
 constexpr uint32_t kResFlag = 0x8000u;     // elist entry: point is reserved in the current complex-mode call
 
 template <int N>
@@ -435,7 +445,7 @@ struct WarpBoard {
                 const bool ok = ent - 1u < 0x7fffu;                 // alive and not reserved
                 const unsigned m = __ballot_sync(kFull, ok);
                 const int c = __popc(m);
-                if (rnd < c) {
+                if (uni(rnd < c)) {
                     const bool hit = ok && __popc(m & ((1u << lane) - 1u)) == rnd;
                     pick = (int)__shfl_sync(kFull, ent, __ffs(__ballot_sync(kFull, hit)) - 1);
                     break;
@@ -453,7 +463,7 @@ struct WarpBoard {
     // iteration wins and exactly its draws (and those before it) are consumed.
     __device__ __forceinline__ int random_piece(int agent) {
         bool complex_mode = false;
-        if (ending) {                                               // :348-351
+        if (uni(ending != 0)) {                                     // :348-351
             if (stones <= kEndingStones) ending = 0;
             else complex_mode = true;
         }
@@ -463,7 +473,7 @@ struct WarpBoard {
             // (:356); inside a playout it always is (it was placed one move ago), and for the first
             // move of a playout the kernel settles that before the loop.
             const int lm = prev;
-            if (lm >= 0) {                                          // :355-380
+            if (uni(lm >= 0)) {                                     // :355-380
                 const Eval f = eval_cells<kEvalAll>(agent, lm + off_cell);
                 unsigned K = 0, S = 0, C = 0;
                 if (f.live) {
@@ -538,7 +548,7 @@ struct WarpBoard {
         const bool single = (int)(w1[root] >> 16) == root;
         const int agent = fCol(w0[root]);                           // colour of the captured string
 #pragma unroll 1
-        for (int k = root; k != kNilP;) {
+        for (int k = root; uni(k != kNilP);) {
             const int nx = fBh(h0[2 * k + 1]);
             stones--;
             if (n_el == kElistCap) { AGB_DEBUG_EVENT(0); compact(); }   // stale entries are dropped
@@ -673,7 +683,7 @@ struct WarpBoard {
             if (d < 4) {
                 const int nb = __shfl_sync(kFull, nb_l, d);
                 const uint32_t v = w0[nb];
-                if (isEmpty(v)) continue;                         // captured earlier in this put
+                if (uni(isEmpty(v))) continue;                    // captured earlier in this put
                 const int sn = fA(v);
                 const uint32_t h = w1[sn] - 1u;                     // sn->hp -= 1
                 w1[sn] = h;
@@ -701,7 +711,7 @@ struct WarpBoard {
                 w1[self] = h;
                 if ((h & 0xffffu) == 0) victim = self;
             }
-            if (victim >= 0) kill_string(victim);
+            if (uni(victim >= 0)) kill_string(victim);
         }
         }
     }
@@ -832,20 +842,20 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
         for (;;) {
             while (bd.gen_end - bd.pos < (uint32_t)WB::kLookahead) bd.refill(a.rng, a.jump);
             const int r = bd.random_piece(colour);
-            if (r >= 0) {
+            if (uni(r >= 0)) {
                 bd.put(colour, r);
                 mv++;
                 if (AMAF) {
                     // mark[r] / mark2[r] = cstep of the FIRST play of that side at r (:304,:319);
                     // only cstep <= AMAF_RANGE is ever used
-                    if (cstep <= kAmafRange) {
+                    if ((cstep <= kAmafRange)) {
                         const uint32_t key = (uint32_t)r | (colour == amaf_agent ? 512u : 0u);
                         bool dup = false;
-                        for (int b0 = 0; b0 < n_log; b0 += 32) {
+                        for (int b0 = 0; uni(b0 < n_log); b0 += 32) {
                             const uint32_t e = b0 + lane < n_log ? amaf_log[b0 + lane] : 0xffffu;
                             dup |= __ballot_sync(kFull, (e & 1023u) == key) != 0;
                         }
-                        if (!dup) { amaf_log[n_log] = (uint16_t)(key | ((uint32_t)cstep << 10)); n_log++; }
+                        if ((!dup)) { amaf_log[n_log] = (uint16_t)(key | ((uint32_t)cstep << 10)); n_log++; }
                     }
                 }
             } else {                                                // Board::pass, Board.cpp:200-203
@@ -856,7 +866,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             const int before = bd.prev;
             bd.prev = r;                                            // Board.cpp:171 / :202
             if (colour != first) {
-                if ((before & r) < 0) break;
+                if (uni((before & r) < 0)) break;
                 if ((int)mv > a.max_moves) { fault = true; break; } // fault detector, once per pair
                 if (AMAF) cstep++;
             }
@@ -871,17 +881,17 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
             atomicAdd(&a.stats[kStatPlayouts], 1ull);
             if (fault) atomicAdd(&a.stats[kStatFaults], 1ull);
         }
-        if (AMAF && !fault) {
+        if (AMAF && uni(!fault)) {
             // :329-338 — point q counts for the agent table when the agent's first play there has
             // cstep <= 40, else for the enemy table when the enemy's has (the `else if`)
             __syncwarp();
             const int w = diff - (a.avrg_dev ? __ldg(a.avrg_dev) : d.avrg_win);
             uint32_t agent_bits = 0;                // bit (q & 31) of lane (q >> 5): agent marked q
-            for (int k = 0; k < n_log; k++) {
+            for (int k = 0; uni(k < n_log); k++) {
                 const uint32_t e = amaf_log[k];
-                if ((e & 512u) && lane == (int)((e & 511u) >> 5)) agent_bits |= 1u << (e & 31u);
+                agent_bits |= ((e & 512u) && lane == (int)((e & 511u) >> 5)) ? 1u << (e & 31u) : 0u;
             }
-            for (int b0 = 0; b0 < n_log; b0 += 32) {
+            for (int b0 = 0; uni(b0 < n_log); b0 += 32) {
                 const bool valid = b0 + lane < n_log;
                 const uint32_t e = valid ? amaf_log[b0 + lane] : 0u;
                 const uint32_t q = e & 511u;
@@ -893,6 +903,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
                     atomicAdd((unsigned long long*)&a.amaf[((size_t)d.amaf_class * (4 * (kAmafRange + 1)) + slot) * WB::NN + row * N + col],
                               (unsigned long long)(long long)w);
                 }
+                __syncwarp();   // one latch (see CONVERGENCE)
             }
         }
         if (lane == 0) {
@@ -908,6 +919,7 @@ __global__ void __launch_bounds__(WARPS * 32, BLOCKS_PER_SM) playout_warp_kernel
                 }
             }
         }
+        __syncwarp();       // one latch for the playout loop (see CONVERGENCE)
     }
 }
 
