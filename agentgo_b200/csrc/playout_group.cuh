@@ -119,10 +119,10 @@ struct GCfg {
     static constexpr int E = kGroupElistCap;        // elist entries, in global memory (kernel_args.h)
     // shared-memory words of one playout: ring | board | cbuf, a multiple of 4
     static constexpr int oRing = 0, oBoard = R / 2, oCbuf = oBoard + NP;
-    // cbuf: G 16-bit entries, the candidates of a move.  The stride from one playout of a warp to the next
+    // cbuf: 2 G 16-bit entries, the candidates of a move (the scan may overshoot the G that are evaluated).  The stride from one playout of a warp to the next
     // is a multiple of 4 words (the ring is written with 128-bit stores) and = 8 mod 32, so that the
     // same field of the four playouts of a warp (cbuf, ring position, board word) sits in different banks.
-    static constexpr int oLog = oCbuf + G / 2;      // AMAF only: kAmafLog 16-bit entries
+    static constexpr int oLog = oCbuf + G;          // AMAF only: kAmafLog 16-bit entries
     static constexpr int words4 = ((oLog + (AMAF ? kAmafLog / 2 : 0) + 3) / 4) * 4;
     static constexpr int words = words4 + ((8 - words4 % 32) + 32) % 32;
     static constexpr int warp_words = NG * words;
@@ -634,27 +634,33 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     if (nb_empty) cbuf[__popc(nmask & lt)] = (uint16_t)((uint32_t)cidx0 | 0x8000u);
                     n_items = n_nb = __popc(nmask);
                 }
-                // pairs whose fate this pass settles: those scanned, or those before the first empty one
-                // that found no room
-                int covered = -1;
-                int b = 0;
+                // A round adds the empty points of G pairs to the items, in draw order.  A playout scans its
+                // first round whatever it holds and a further one only with fewer than G items, and a round adds
+                // at most G: the candidate buffer has 2 G entries, the items are its first G, and entry G — the
+                // first empty point that found no room — says where the pass ends.
+                int b = 0, bend = 0;
+                const int cap = min(G, n_items + kWant);                // scan until the pass holds this many items
+                const int blim = min(kScan, lim);
+                bool scan = rej;
 #pragma unroll 1
                 do {
                     const int jp = b + gl;
                     const uint32_t row = mod_small<C::N>(ring[(pos + off18 + 2u * (uint32_t)jp) & RM]);
                     const uint32_t cl = mod_small<C::N>(ring[(pos + off18 + 2u * (uint32_t)jp + 1u) & RM]);
                     const int ridx = (int)(row * W + cl) + (W + 1);
-                    const bool can = rej && covered < 0 && jp < lim && isEmpty(w[ridx]);
+                    const bool can = scan && jp < lim && isEmpty(w[ridx]);
                     const unsigned emask = (__ballot_sync(kFull, can) >> gbase) & C::GM;
-                    const int rank = n_items + __popc(emask & lt);
-                    if (can && rank < G) cbuf[rank] = (uint16_t)((uint32_t)ridx | ((uint32_t)jp << 9));
-                    const unsigned over = (__ballot_sync(kFull, can && rank == G) >> gbase) & C::GM;
-                    if (over) covered = b + __ffs(over) - 1;
-                    n_items = min(G, n_items + __popc(emask));
+                    if (can) cbuf[n_items + __popc(emask & lt)] = (uint16_t)((uint32_t)ridx | ((uint32_t)jp << 9));
+                    n_items += __popc(emask);
                     b += G;
-                } while (b < kScan && __any_sync(kFull, rej && covered < 0 && n_items < G && n_items - n_nb < kWant && b < lim));
-                if (covered < 0) covered = b;
+                    if (scan) bend = b;
+                    scan = scan && n_items < cap && b < blim;
+                } while (__any_sync(kFull, scan));
                 __syncwarp();
+                // pairs whose fate this pass settles: those scanned, or those before the first empty one
+                // that found no room
+                const int covered = n_items > G ? (int)(((uint32_t)cbuf[G] >> 9) & 31u) : bend;
+                n_items = min(n_items, G);
                 const bool has = gl < n_items;
                 const uint32_t item = has ? (uint32_t)cbuf[gl] : (uint32_t)(W + 1);
                 const Ev e = eval_point<W, kEvAll>(w, colour, (int)(item & 511u), ko_key);
