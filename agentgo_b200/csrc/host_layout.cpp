@@ -49,7 +49,8 @@ void to_padded(const Position& p, PaddedPosition* out) {
 
 // The one-word layout of the group kernel (kernel_args.h).
 void to_group(const Position& p, GroupPosition* out) {
-    const int n = p.n, w = n + 2;
+    // one border column: rows of n + 1 points (GCfg in playout_group.cuh)
+    const int n = p.n, w = n + 1;
     auto pad = [&](int idx) { return (idx / n + 1) * w + (idx % n + 1); };
     for (int i = 0; i < kMaxNP; i++) out->w[i] = gw::border((uint32_t)i);
     for (int idx = 0; idx < n * n; idx++) {

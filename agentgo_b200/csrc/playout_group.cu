@@ -38,7 +38,7 @@ cudaError_t launch_g(const KernelArgs& a, int sm_count, cudaStream_t s, LaunchIn
 }  // namespace
 
 cudaError_t launch_playout_group(int n, int lanes, const KernelArgs& a, int sm_count, cudaStream_t s, LaunchInfo* info) {
-    // 8 lanes per playout: 100 playouts per SM (2 304 B of shared memory each at 19x19) in one block of
+    // 8 lanes per playout: 100 playouts per SM (2 224 B of shared memory each at 19x19) in one block of
     // 25 warps, 80 registers; 16 lanes: 64 playouts in 32 warps of 64 registers; 32 lanes (the mapping
     // of playout_warp.cu run through this code, for comparison): 32 playouts in 32 warps.
     if (lanes == 8 && a.amaf) {
@@ -52,9 +52,9 @@ cudaError_t launch_playout_group(int n, int lanes, const KernelArgs& a, int sm_c
         return cudaErrorInvalidValue;       // the marks are recorded with 8 lanes per playout (or by the warp kernel)
     } else if (lanes == 8) {
         switch (n) {
-            case 9: return launch_g<9, 8, 24, 1>(a, sm_count, s, info);
-            case 13: return launch_g<13, 8, 24, 1>(a, sm_count, s, info);
-            case 19: return launch_g<19, 8, 24, 1>(a, sm_count, s, info);
+            case 9: return launch_g<9, 8, 25, 1>(a, sm_count, s, info);
+            case 13: return launch_g<13, 8, 25, 1>(a, sm_count, s, info);
+            case 19: return launch_g<19, 8, 25, 1>(a, sm_count, s, info);
         }
     } else if (lanes == 16) {
         switch (n) {

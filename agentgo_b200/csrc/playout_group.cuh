@@ -116,18 +116,28 @@ struct GCfg {
     static constexpr int N = N_, G = G_, SEG = SEG_;
     static constexpr bool AMAF = AMAF_;
     static constexpr int kAmafLog = 80;             // first plays with cstep <= 40: at most 78
-    static constexpr int W = N + 2, NP = W * W, NN = N * N, NG = 32 / G;
+    // The padded board has ONE border column: the point right of a row's last point is the point left of
+    // the next row's first, and both are border.  Rows -1 .. N of N + 1 points each, and one more point
+    // for the lower right diagonal of the last point: (N + 1)(N + 2) + 1 words (421 at 19x19; two border
+    // columns took 441, and the 80 B are the difference between 24 and 25 warps per SM).
+    static constexpr int W = N + 1, NP = W * (N + 2) + 1, NN = N * N, NG = 32 / G;
     static constexpr int BATCH = G * SEG;           // draws per refill of one playout
     static constexpr int R = 2 * BATCH;             // ring entries
     static constexpr int E = kGroupElistCap;        // elist entries, in global memory (kernel_args.h)
     // shared-memory words of one playout: ring | board | cbuf, a multiple of 4
     static constexpr int oRing = 0, oBoard = R / 2, oCbuf = oBoard + NP;
-    // cbuf: 2 G 16-bit entries, the candidates of a move (the scan may overshoot the G that are evaluated).  The stride from one playout of a warp to the next
-    // is a multiple of 4 words (the ring is written with 128-bit stores) and = 8 mod 32, so that the
-    // same field of the four playouts of a warp (cbuf, ring position, board word) sits in different banks.
-    static constexpr int oLog = oCbuf + G;          // AMAF only: kAmafLog 16-bit entries
+    // cbuf: G + 1 16-bit entries: the candidates of a move, and the first one that found no room (where
+    // the pass ends).  The stride from one playout of a warp to the next is a multiple of 4 words (the
+    // ring is written with 128-bit stores) and such that the same field of the playouts of a warp
+    // (cbuf, ring position, board word) sits in different banks: k * words is no multiple of 32 for 0 < k < NG.
+    static constexpr int oLog = oCbuf + (G + 2) / 2;    // AMAF only: kAmafLog 16-bit entries
     static constexpr int words4 = ((oLog + (AMAF ? kAmafLog / 2 : 0) + 3) / 4) * 4;
-    static constexpr int words = words4 + ((8 - words4 % 32) + 32) % 32;
+    static constexpr bool spread(int w) {
+        for (int k = 1; k < NG; k++) if ((k * w) % 32 == 0) return false;
+        return true;
+    }
+    static constexpr int pick_words(int w) { return spread(w) ? w : pick_words(w + 4); }
+    static constexpr int words = pick_words(words4);
     static constexpr int warp_words = NG * words;
     static constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
 };
@@ -655,10 +665,9 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     if (nb_empty) cbuf[__popc(nmask & lt)] = (uint16_t)((uint32_t)cidx0 | 0x8000u);
                     n_items = n_nb = __popc(nmask);
                 }
-                // A round adds the empty points of G pairs to the items, in draw order.  A playout scans its
-                // first round whatever it holds and a further one only with fewer than G items, and a round adds
-                // at most G: the candidate buffer has 2 G entries, the items are its first G, and entry G — the
-                // first empty point that found no room — says where the pass ends.
+                // A round adds the empty points of G pairs to the items, in draw order.  The items are the first
+                // G entries of the candidate buffer; entry G — the first empty point that found no room — says
+                // where the pass ends (further ones are not stored).
                 int b = 0, bend = 0;
                 const int cap = min(G, n_items + kWant);                // scan until the pass holds this many items
                 const int blim = min(kScan, lim);
@@ -671,7 +680,8 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     const int ridx = (int)(row * W + cl) + (W + 1);
                     const bool can = scan && jp < lim && isEmpty(w[ridx]);
                     const unsigned emask = (__ballot_sync(kFull, can) >> gbase) & C::GM;
-                    if (can) cbuf[n_items + __popc(emask & lt)] = (uint16_t)((uint32_t)ridx | ((uint32_t)jp << 9));
+                    const int rank = n_items + __popc(emask & lt);
+                    if (can && rank <= G) cbuf[rank] = (uint16_t)((uint32_t)ridx | ((uint32_t)jp << 9));
                     n_items += __popc(emask);
                     b += G;
                     if (scan) bend = b;
