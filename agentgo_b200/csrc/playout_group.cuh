@@ -73,6 +73,9 @@
 #ifndef AGB_NBFILTER
 #define AGB_NBFILTER 1
 #endif
+#ifndef AGB_WALK_UNROLL
+#define AGB_WALK_UNROLL 4
+#endif
 
 namespace agb {
 namespace grp {
@@ -858,17 +861,21 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     w[tail] = setNext(tw, target);
                 }
                 // strings F_1..F_(k-1) are relabelled to Fk (:284-289), each by its own lane
-                bool walk = own && root != fk;
-                uint32_t cur = root;
+                // (8 % of the kernel's instructions were this loop: walks are 15 stones long on average, so
+                // four steps per vote; the flag is an int — a bool that lives across the loop is kept as a
+                // byte and costs three PRMT per test — and the cursor is the byte offset of the stone's word)
+                int walk = (own && root != fk) ? 1 : 0;
+                uint32_t cur = 4u * root;
+                const uint32_t tail4 = 4u * tail, fkA = fk << gw::kAShift;
 #pragma unroll 1
-                while (__any_sync(kFull, walk)) {
+                while (__any_sync(kFull, walk != 0)) {
 #pragma unroll
-                    for (int u = 0; u < 2; u++)
+                    for (int u = 0; u < AGB_WALK_UNROLL; u++)
                         if (walk) {
-                            const uint32_t cw = w[cur];
-                            w[cur] = setA(cw, fk);
-                            walk = cur != tail;
-                            cur = fNext(cw);
+                            const uint32_t cw = at(w, cur);
+                            *reinterpret_cast<uint32_t*>(reinterpret_cast<char*>(w) + cur) = (cw & ~kAMask) | fkA;
+                            walk = cur != tail4 ? 1 : 0;
+                            cur = (cw >> (gw::kNextShift - 2)) & (511u << 2);
                         }
                 }
                 __syncwarp();
