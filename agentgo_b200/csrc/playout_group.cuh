@@ -474,12 +474,13 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
     enum { kFetch = 0, kPlay = 1, kEnded = 2, kDone = 3 };
     int phase = kFetch;
     uint32_t colour = 1;
-    bool closes = false;        // the move about to be made closes a pair (it is the second mover's)
+    // (flags that live across a loop are ints: a bool is kept as a byte and costs a PRMT or two per test)
+    int closes = 0;             // the move about to be made closes a pair (it is the second mover's)
     int prev = -1, stones = 0, ko_key = -1, ending = 0, n_el = 0, n_dead = -1;
     uint32_t pos = 0, mv = 0;
     GenState gs = {0, 0, 0, 0, 0};
     uint32_t unit = 0;          // which of this shard's units (the engine keeps a launch below 2^32 of them)
-    bool fault = false;
+    int fault = 0;
     // AMAF marks: a log of the first plays with cstep <= 40 (key = point | 512 for the agent's), resolved
     // when the playout ends; cstep is 2 in the first pair (:293,:297)
     constexpr int kAmafRange = 40;      // AMAF_RANGE, GoContest/AgentGo.h:16
@@ -583,7 +584,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 if (grp == X) {
                     phase = kPlay;
                     colour = (uint32_t)d.first;
-                    closes = false;
+                    closes = 0;
                     prev = lm;
                     stones = gp.stones;
                     ko_key = gp.ko_key_col > 0 ? ((gp.ko_key_col << 16) | gp.ko_idx) : -1;
@@ -592,7 +593,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     n_dead = -1;
                     pos = 0; mv = 0;
                     gs.g0 = t.s0; gs.g1 = t.s1; gs.g2 = t.s2; gs.g3 = t.s3; gs.gen_end = 0;
-                    unit = (uint32_t)l; fault = false;
+                    unit = (uint32_t)l; fault = 0;
                     n_log = 0; cstep = 2; amaf_agent = (uint32_t)d.agent;
                 }
             } else if (grp == X) {
@@ -608,10 +609,10 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
         }
 
         // ---- Board::getRandomPiece, Board.cpp:341-411 ----
-        bool cplx = false;
+        int cplx = 0;
         if (ending) {                                                           // :348-351
             if (stones <= kEndingStones) ending = 0;
-            else cplx = true;
+            else cplx = 1;
         }
         const bool search = live && !cplx;
         if (search) n_dead = -1;                                                // put stops maintaining elist
@@ -635,7 +636,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                                                 // more scan round costs a fifth of one more pass
             int lim = kEndingThreshold - 1;     // rejection pairs that may still be accepted: the 100th draw is
                                                 // consumed but never accepted (:402-405)
-            bool rej = search;
+            int rej = search ? 1 : 0;
             bool first_pass = true;
             const unsigned lt = (1u << gl) - 1u;
 #pragma unroll 1
@@ -674,7 +675,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                 int b = 0, bend = 0;
                 const int cap = min(G, n_items + kWant);                // scan until the pass holds this many items
                 const int blim = min(kScan, lim);
-                bool scan = rej;
+                int scan = rej;
 #pragma unroll 1
                 do {
                     const int jp = b + gl;
@@ -688,7 +689,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     n_items += __popc(emask);
                     b += G;
                     if (scan) bend = b;
-                    scan = scan && n_items < cap && b < blim;
+                    scan = (scan && n_items < cap && b < blim) ? 1 : 0;
                 } while (__any_sync(kFull, scan));
                 __syncwarp();
                 // pairs whose fate this pass settles: those scanned, or those before the first empty one
@@ -737,7 +738,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                             pos += 2u * (uint32_t)(k + 1);
                             r = (G == 8 && k == 8) ? pt8 : ptk;
                             found = true;
-                            rej = false;
+                            rej = 0;
                         }
                     }
                 }
@@ -748,13 +749,13 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                     if (goodr) {
                         r = (int)(win & 511u);
                         found = true;
-                        rej = false;
+                        rej = 0;
                         pos += 2u * (((win >> 9) & 31u) + 1u);
                     } else {
                         const int used = min(covered, lim + 1);                // pairs consumed by this pass
                         pos += 2u * (uint32_t)used;
                         lim -= used;
-                        if (lim < 0) { ending = 1; cplx = true; rej = false; }
+                        if (lim < 0) { ending = 1; cplx = 1; rej = 0; }
                     }
                 }
                 first_pass = false;
@@ -975,11 +976,11 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
             prev = r;                                                           // Board.cpp:171 / :202
             if (closes) {
                 if ((before & r) < 0) phase = kEnded;
-                else if ((int)mv > a.max_moves) { fault = true; phase = kEnded; }   // fault detector, once per pair
+                else if ((int)mv > a.max_moves) { fault = 1; phase = kEnded; }   // fault detector, once per pair
                 if (C::AMAF) cstep++;
             }
             colour = 3u - colour;
-            closes = !closes;
+            closes ^= 1;
         }
         // (see the convergence note at the top of the file: one latch for the loop)
         __syncwarp();
