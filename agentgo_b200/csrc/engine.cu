@@ -157,14 +157,14 @@ int Engine::launch(const std::vector<Position>& starts, const std::vector<StartD
     const int64_t total = (int64_t)S * P;
     const int64_t local_units = total > sh_rank ? (total - sh_rank + sh_count - 1) / sh_count : 0;
     // Lanes per playout of the group kernel, 0 = another kernel.  AGB_KERNEL_AUTO: the group kernel (four playouts per warp) has the higher THROUGHPUT
-    // (+9 % at 19x19), the warp kernel the lower LATENCY per playout (a warp serves one playout, not
-    // four in lock step), so a launch of less than about two loads of the machine (100 playouts per SM)
-    // finishes earlier on the warp kernel: 0.8 ms against 2.6 ms for 2 000 playouts at 19x19, equal at
-    // 32 000 (tests/latency_probe.py).  The reference's own genmove is 25 850 playouts.  On 9x9 a playout is
-    // 100 moves and the serial sections are short: the warp kernel wins at every size (20.2 M against 19.0 M
-    // playouts/s, profiles/r02_quick_bench.txt).
+    // (+23 % at 19x19), the warp kernel the lower LATENCY per playout (a warp serves one playout, not
+    // four in lock step), so a launch of less than about one load of the machine (100 playouts per SM)
+    // finishes earlier on the warp kernel: 0.7 ms against 2.3 ms for 2 000 playouts at 19x19, equal at
+    // 16 000, 9.4 against 11.5 ms at 64 000 (tests/latency_probe.py, profiles/r02_latency_probe.txt).  The
+    // reference's own genmove is 25 850 playouts.  On 9x9 a playout is 100 moves and the serial sections are
+    // short: the warp kernel wins at every size (21.0 M against 20.4 M playouts/s, profiles/r02_quick_bench.txt).
     int group_lanes = 0;
-    const bool big = local_units >= 2 * (int64_t)sm_count_ * 100 && board.n() > 9;
+    const bool big = local_units >= (int64_t)sm_count_ * 110 && board.n() > 9;
     if (cfg.kernel == AGB_KERNEL_GROUP8) group_lanes = 8;
     else if (cfg.kernel == AGB_KERNEL_AUTO) group_lanes = big ? 8 : 0;
     else if (cfg.kernel == AGB_KERNEL_GROUP16 && !want_amaf) group_lanes = 16;      // (the AMAF marks: 8 lanes per

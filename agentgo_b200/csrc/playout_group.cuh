@@ -45,7 +45,7 @@
 //    memory (L2): only complex mode and compaction read it, all 32 lanes at a time, and the 752 B
 //    it took per playout were five warps per SM.  The rand() ring is smaller than the warp kernel's
 //    (R = 2*G*SEG entries) and refilled whenever a phase is about to read past its end.  State per
-//    playout in shared memory: 2 304 B at 19x19, 100 playouts = 25 warps per SM.
+//    playout in shared memory: 2 224 B at 19x19, 100 playouts = 25 warps per SM.
 //
 // Restates Board.cpp:68-177 (put), :293-339 (killSetNode), :341-411 (getRandomPiece), :413-478
 // (getRandomPieceComplex), :480-755 (predicates), :910-925 (countScore) and the pair loops of
@@ -379,7 +379,7 @@ AGB_NOINLINE int complex_pick(uint32_t* w, uint16_t* elist, int n_el, int spaces
     if (range != 0) {
         int rnd = (int)(draw % (uint32_t)range);
         *used = 1;
-        bool found = false;
+        int found = 0;
         // list order = the array from its end: first what is beyond the registers ...
 #pragma unroll 1
         for (int top = n_el - 1; top >= 32 * kKeep && !found; top -= 32) {
@@ -391,7 +391,7 @@ AGB_NOINLINE int complex_pick(uint32_t* w, uint16_t* elist, int n_el, int spaces
             if (rnd < c) {
                 const bool hit = ok && __popc(m & ((1u << lane) - 1u)) == rnd;
                 pick = (int)__shfl_sync(kFull, ent, __ffs(__ballot_sync(kFull, hit)) - 1);
-                found = true;
+                found = 1;
             } else {
                 rnd -= c;
             }
@@ -407,7 +407,7 @@ AGB_NOINLINE int complex_pick(uint32_t* w, uint16_t* elist, int n_el, int spaces
                     // the rnd-th from the top is the (c-1-rnd)-th from the bottom
                     const bool hit = ok && __popc(m & ((1u << lane) - 1u)) == c - 1 - rnd;
                     pick = (int)(__shfl_sync(kFull, ents[r], __ffs(__ballot_sync(kFull, hit)) - 1) & 0x1ffu);
-                    found = true;
+                    found = 1;
                 } else {
                     rnd -= c;
                 }
@@ -899,7 +899,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
             // group give the liberty back to the strings around it (increments commute: atomics)
             if (__any_sync(kFull, caps != 0)) {
                 uint32_t kcur = kNilG;
-                bool single = false;
+                int single = 0;
 #pragma unroll 1
                 for (;;) {
                     const bool want = kcur == kNilG && caps != 0;
@@ -908,7 +908,7 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                         if (want) {
                             caps &= caps - 1u;
                             kcur = victim;
-                            single = fNext(w[victim]) == kNilG;
+                            single = fNext(w[victim]) == kNilG ? 1 : 0;
                         }
                     }
                     if (!__any_sync(kFull, kcur != kNilG)) break;

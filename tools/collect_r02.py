@@ -17,7 +17,7 @@ fill = [v for k, v in per.items() if "FillFunctor" in k[1]]
 m = json.load(open("profiles/r02_mappings.json"))["group8"]
 dur = statistics.mean(v["gpu__time_duration.sum"] for v in play) / 1e6
 fd = statistics.mean(v["gpu__time_duration.sum"] for v in fill) / 1e6 if fill else 0.0
-json.dump({"kernel": "playout_group_kernel<GCfg<19, 8 lanes per playout, 16 draws per lane>, 24 warps, 1 block per SM>",
+json.dump({"kernel": "playout_group_kernel<GCfg<19, 8 lanes per playout, 16 draws per lane>, 25 warps, 1 block per SM>",
            "launches": len(play),
            "dram_bytes_per_launch": statistics.median(v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"] for v in play),
            "ms_per_launch_under_ncu": dur, "l2_flush_fill_ms": fd, "kernel_share_of_step": dur / (dur + fd),
