@@ -39,7 +39,9 @@ struct PaddedPosition {
 };
 
 // Device layout of a start position for the group kernel (playout_group.cuh): ONE word per point of
-// the padded board,
+// a padded board with ONE border column — rows -1 .. n of n + 1 points each, the point right of a row's
+// last point being the point left of the next row's first; (n + 1)(n + 2) + 1 words (to_group in
+// host_layout.cpp, GCfg in playout_group.cuh) —
 //   bits 0-1 colour | bits 2-10 A | bits 11-19 next | bits 21-31 F
 //        stone:  A = root of its string, next = next stone of the string (511 = end),
 //                F = pseudo-liberties at the root stone / the string's last stone at its SECOND stone

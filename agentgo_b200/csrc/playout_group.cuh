@@ -13,9 +13,8 @@
 //  * CONTROL FLOW IS WARP-UNIFORM.  Every loop bound and every branch around a collective is
 //    derived from a ballot / any over the whole warp; what differs between the playouts of a
 //    warp is DATA (predicates per group).  Every collective therefore runs with the full mask in
-//    converged code — no divergent collectives, none of the BSSY/BSYNC/WARPSYNC scaffolding the
-//    compiler had to put around the collectives of the warp kernel.  tests/csrc/simt_emu.h runs
-//    this very source on the CPU and aborts if any lane reaches a collective at another site.
+//    converged code.  tests/csrc/simt_emu.h runs this very source on the CPU and aborts if any lane
+//    reaches a collective at another site.
 //    CONVERGENCE NOTE.  ptxas has to PROVE the convergence, or it guards every collective of the kernel
 //    with UMOV + BRA.DIV and a WARPSYNC.COLLECTIVE slow path (8 % of the executed instructions, a
 //    quarter of the code).  Two things defeated the proof and are avoided (found by cutting the kernel
@@ -29,7 +28,8 @@
 //  * RARE BULK WORK BORROWS THE WHOLE WARP.  Clone, scoring, complex mode
 //    (Board::getRandomPieceComplex) and the compaction of the empty-point array serve one group at
 //    a time with all 32 lanes (the board of any group of the warp is in reach of every lane).
-//  * One 32-bit word per point (the warp kernel had two), padded (N+2)^2 board (kernel_args.h, gw::):
+//  * One 32-bit word per point (the warp kernel had two) of a padded board with ONE border column (GCfg;
+//    word layout: kernel_args.h, gw::):
 //        bits 0-1   colour (0 empty, 1 black, 2 white, 3 border)
 //        bits 2-10  A     stone: root of its string; empty / border point: its own index
 //        bits 11-19 next  stone: next stone of the string in SetNode::pieces order (511 = end);
