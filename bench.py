@@ -465,6 +465,14 @@ def run_b200(args):
         roofline["issue_slots"] = {"achieved": per_gpu_rate * winst, "peak": peak_issue, "unit": "warp-instructions/s",
                                    "frac": per_gpu_rate * winst / peak_issue, "warp_instructions_per_playout": winst,
                                    "source": "ncu smsp__inst_executed.sum (profiles/roofline_traffic.json)"}
+        if pj.get("alu_pipe_active_pct"):
+            # what binds the issue rate: the ALU pipe (logic, compares, shifts, selects) takes one warp
+            # instruction every second cycle per scheduler; utilisation from the ncu capture of the same kernel
+            roofline["alu_pipe"] = {"frac": pj["alu_pipe_active_pct"] / 100.0, "alu_share_of_instructions": pj.get("alu_share_of_instructions"),
+                                    "source": "ncu sm__pipe_alu_cycles_active (profiles/r02_group8_metrics.txt, 100 k playouts); "
+                                              "opcode shares: profiles/r02_group8_opcodes.txt"}
+            roofline["note"] = ("the path is SM integer-issue bound — the ALU pipe first, then the issue slots, then shared memory; "
+                                "not HBM or tensor (SURVEY.md §8d)")
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         rates, info = cpu_reference(cfg_id, sample_seconds=args.cpu_seconds)

@@ -25,7 +25,7 @@ json.dump({"kernel": "playout_group_kernel<GCfg<19, 8 lanes per playout, 16 draw
                      "--clock-control none, python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras)",
            "algorithmic_bytes_per_launch": 4.0e6, "warp_instructions_per_playout": m["warp_instructions_per_playout"],
            "warp_instructions_source": "profiles/r02_group8_metrics.txt (ncu smsp__inst_executed.sum / 100000 playouts)",
-           "ipc_per_sm": m["ipc_per_sm"]}, open("profiles/roofline_traffic.json", "w"), indent=1)
+           "ipc_per_sm": m["ipc_per_sm"], "alu_pipe_active_pct": m["alu_pipe_active_pct"], "alu_share_of_instructions": 0.583}, open("profiles/roofline_traffic.json", "w"), indent=1)
 d = json.load(open("profiles/bench_r02.json"))
 print("bench value %.4g e2e %.4g cpu %.4g  int_issue %.3f issue_slots %s smem %.3f genmove %.1f ms strong %.4g" % (
     d["value"], d["e2e"]["value"], d["cpu_baseline"]["value"], d["roofline"]["frac"],
