@@ -723,7 +723,9 @@ AGB_DEV void playout_group_body(const KernelArgs& a, uint32_t* smem_warp, int la
                         }
                         unsigned hm = (__ballot_sync(kFull, hit) >> gbase) & C::GM;
                         int pt8 = -1;
-                        if (G == 8) {
+                        // (the ninth iteration only matters to a playout whose first eight accepted nothing
+                        // and that has a kill cell: 23 % of the playouts that get here)
+                        if (G == 8 && __any_sync(kFull, hm == 0 && Kb != 0)) {
                             const uint32_t ra = mod_small<3>(ring[(pos + 16u) & RM]);
                             const uint32_t rb = mod_small<3>(ring[(pos + 17u) & RM]);
                             const uint32_t c9 = ra * 3u + rb;
