@@ -82,7 +82,8 @@ typedef enum agb_status {
 
 /* kernel selector: the mapping of playouts onto the machine */
 typedef enum agb_kernel {
-    AGB_KERNEL_AUTO = 0,
+    AGB_KERNEL_AUTO = 0,    /* per launch: GROUP8 from about one load of the machine up (110 playouts per SM,
+                               boards larger than 9x9), else WARP (lower latency per playout) */
     AGB_KERNEL_THREAD = 1,  /* one thread per playout */
     AGB_KERNEL_WARP = 2,    /* one warp per playout   */
     AGB_KERNEL_GROUP8 = 3,  /* four playouts per warp, 8 lanes each  */
