@@ -63,6 +63,34 @@ def test_midgame_golden():
         assert (d == g["diffs"][bi][:P]).all()
 
 
+def test_random_positions_match_oracle(port_lib):
+    """Random positions of every length (openings with all eight neighbourhood cells empty, crowded
+    endgames in complex mode, stones on edges and corners of the one-border-column board), root and
+    candidate mode, against the oracle — the CPU-side counterpart of tests/soak_parity.py."""
+    emu = emu_group()
+    po = port_lib
+    rng = np.random.RandomState(11)
+    for k in range(18):
+        n = [9, 13, 19][k % 3]
+        length = int(rng.randint(0, 3 * n * n))
+        mv = po.OracleBoard(n, "port").random_game(1 + k % 2, length, 2000 + k)
+        ob = po.OracleBoard(n, "port").replay(mv)
+        st = ob.export_state()
+        empties = [i for i in range(n * n) if st[16 + i] == 0]
+        if not empties:
+            continue
+        colour = 1 + (k // 3) % 2
+        P = 12
+        orr = ob.playouts(colour, None, P, seed_base=k, position_id=k, threads=0)
+        o, d, s, _ = emu_playouts(emu, n, 8, mv, colour, None, P, seed_base=k, position_id=k)
+        assert (d == orr[3]).all(), (k, n, length)
+        cands = [(i // n, i % n) for i in empties[::max(1, len(empties) // 3)]][:3]
+        ow, osp, osn, od = ob.playouts(colour, cands, P, avrg_win=1, seed_base=k, position_id=k, threads=0)
+        for ci, c in enumerate(cands):
+            o, d, s, _ = emu_playouts(emu, n, 8, mv, colour, c, P, avrg_win=1, seed_base=k, position_id=k, cand_idx=ci)
+            assert (d == od[ci]).all() and (o[0], o[1], o[2]) == (ow[ci], osp[ci], osn[ci]), (k, n, length, c)
+
+
 def test_lane_order_does_not_matter():
     """EMU_SHUFFLE runs the lanes of the emulated warp in a random order between two collectives: a
     shared-memory hand-over between lanes without a __syncwarp() would change results."""
