@@ -119,3 +119,21 @@ extern "C" long long emu_group_playouts(int n, int lanes, const uint32_t* moves,
     for (int i = 0; i < kStatCount; i++) stat4[i] = (int64_t)stats[i];
     return (long long)(emu::collectives_run() - before);
 }
+
+// The start position in the group kernel's device layout (kernel_args.h, GroupPosition), for the layout
+// test: words[(n + 1)(n + 2) + 1], elist[n * n] (16-bit entries widened), scal[8] = n_el, stones,
+// ko_key_col, ko_idx, last[0], last[1], ending, words per playout of GCfg<n, 8>.  Returns the word count.
+extern "C" int emu_group_layout(int n, const uint32_t* moves, int n_moves, uint32_t* words, uint32_t* elist, int32_t* scal) {
+    HostBoard hb(n);
+    if (hb.replay(moves, n_moves)) return -1;
+    GroupPosition gp;
+    to_group(hb.position(), &gp);
+    const int np = (n + 1) * (n + 2) + 1;
+    for (int i = 0; i < np; i++) words[i] = gp.w[i];
+    const uint16_t* el = reinterpret_cast<const uint16_t*>(gp.elist_w);
+    for (int i = 0; i < n * n; i++) elist[i] = el[i];
+    scal[0] = gp.n_el; scal[1] = gp.stones; scal[2] = gp.ko_key_col; scal[3] = gp.ko_idx;
+    scal[4] = gp.last[0]; scal[5] = gp.last[1]; scal[6] = gp.ending;
+    scal[7] = n == 9 ? grp::GCfg<9, 8, kJumpSteps>::words : (n == 13 ? grp::GCfg<13, 8, kJumpSteps>::words : grp::GCfg<19, 8, kJumpSteps>::words);
+    return np;
+}

@@ -91,6 +91,58 @@ def test_random_positions_match_oracle(port_lib):
             assert (d == od[ci]).all() and (o[0], o[1], o[2]) == (ow[ci], osp[ci], osn[ci]), (k, n, length, c)
 
 
+def test_device_layout_of_a_position(port_lib):
+    """The one-word-per-point layout the group kernel starts from (kernel_args.h): ONE border
+    column — the point right of a row's last point is the point left of the next row's first —, colours
+    and string structure of the oracle's board, liberties at the roots, the string's last stone at its
+    second stone, the empty-point array in the order of the reference's space_list."""
+    import ctypes as C
+    emu = emu_group()
+    po = port_lib
+    for n, nmoves in ((9, 40), (13, 90), (19, 230)):
+        mv = np.ascontiguousarray(po.OracleBoard(n, "port").random_game(1, nmoves, 77 + n), dtype=np.uint32)
+        st = po.OracleBoard(n, "port").replay(mv).export_state()
+        W, NP = n + 1, (n + 1) * (n + 2) + 1
+        words = np.zeros(NP, dtype=np.uint32)
+        elist = np.zeros(n * n, dtype=np.uint32)
+        scal = np.zeros(8, dtype=np.int32)
+        assert emu.emu_group_layout(n, mv.ctypes.data_as(C.c_void_p), len(mv), words.ctypes.data_as(C.c_void_p),
+                                    elist.ctypes.data_as(C.c_void_p), scal.ctypes.data_as(C.c_void_p)) == NP
+        pad = lambda i: (i // n + 1) * W + (i % n + 1)
+        col, A, nxt, F = words & 3, (words >> 2) & 511, (words >> 11) & 511, words >> 21
+        on_board = {pad(i) for i in range(n * n)}
+        data, root, hp, nis = st[16:16 + n * n], st[16 + n * n:16 + 2 * n * n], st[16 + 2 * n * n:16 + 3 * n * n], st[16 + 4 * n * n:16 + 5 * n * n]
+        for q in range(NP):
+            if q not in on_board:
+                assert col[q] == 3 and A[q] == q and F[q] == 1           # border: its own root, "one liberty"
+        for i in range(n * n):
+            q = pad(i)
+            assert col[q] == data[i]
+            r, c = divmod(i, n)
+            # the four neighbours are one word away in each direction; off the board they are border
+            for dr, dc, off in ((-1, 0, -W), (0, -1, -1), (1, 0, W), (0, 1, 1)):
+                inside = 0 <= r + dr < n and 0 <= c + dc < n
+                assert (col[q + off] != 3) == inside
+                if inside:
+                    assert q + off == pad((r + dr) * n + c + dc)
+            if data[i] == 0:
+                assert A[q] == q and F[q] == 1 and elist[(words[q] >> 11) & 1023] == q
+            else:
+                assert A[q] == pad(int(root[i]))
+                assert nxt[q] == (511 if nis[i] < 0 or nis[i] >= n * n else pad(int(nis[i])))
+                if root[i] == i:
+                    assert F[q] == hp[i]
+                    if nxt[q] != 511:                                       # the second stone names the last one
+                        last = q
+                        while nxt[last] != 511:
+                            last = nxt[last]
+                        assert F[nxt[q]] == last
+        assert scal[0] == (data == 0).sum() and scal[1] == (data != 0).sum()
+        # 2 224 B per playout at 19x19: ring 128 + board 421 + candidates 5 words, bank-spreading stride
+        if n == 19:
+            assert scal[7] * 4 == 2224
+
+
 def test_lane_order_does_not_matter():
     """EMU_SHUFFLE runs the lanes of the emulated warp in a random order between two collectives: a
     shared-memory hand-over between lanes without a __syncwarp() would change results."""
